@@ -1,0 +1,259 @@
+// ctx.cuh -- context, slab geometry and shared device helpers of libeasysimp_b200.so
+//
+// Data layout in HBM (structured grids), chosen for the x-slab partition and for coalesced
+// lane-along-z access; it is NOT the reference's layout (Ferrite numbers dofs by first
+// encounter in cell order, FiniteElementAnalysis.jl:257-279) -- api.cu permutes once at the
+// boundary:
+//   node vectors   v[lp][c][j][k]   lp = local x node plane, c = component, j = y, k = z (fastest)
+//                  -> one x-plane (all 3 components) is ONE contiguous block of 3*plane doubles,
+//                     so the halo exchanged with a neighbour slab needs no packing and the dofs a
+//                     rank owns are one contiguous range (dot products run over it directly).
+//   cell arrays    a[le][j][k]      le = local x element layer
+//   node mask      m[lp][j][k]      uint8, bit c set = dof (node, c) is prescribed
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/easysimp_b200.h"
+
+#define ESIMP_CUDA(call)                                                                         \
+    do {                                                                                         \
+        cudaError_t _e = (call);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            return esimp_fail(ctx, ESIMP_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+        }                                                                                        \
+    } while (0)
+#define ESIMP_TRY(expr)              \
+    do {                             \
+        int _s = (expr);             \
+        if (_s < 0) return _s;       \
+    } while (0)
+
+// geometry of the slab this rank holds (all ints fit 32 bit; flat indices are 64 bit)
+struct GridDev {
+    int nx, ny, nz;        // global element counts
+    int NPX;               // local node planes stored
+    int NEX;               // local element layers stored
+    int gp0;               // global x index of local node plane 0
+    int ge0;               // global x index of local element layer 0
+    int e2p;               // local plane of the low face of local layer le = le + e2p
+    long long plane;       // (ny+1)*(nz+1)
+    long long eplane;      // ny*nz
+    __host__ __device__ long long dof(int lp, int c, int j, int k) const {
+        return ((long long)(lp * 3 + c) * (ny + 1) + j) * (nz + 1) + k;
+    }
+    __host__ __device__ long long node(int lp, int j, int k) const {
+        return ((long long)lp * (ny + 1) + j) * (nz + 1) + k;
+    }
+    __host__ __device__ long long cell(int le, int j, int k) const {
+        return ((long long)le * ny + j) * nz + k;
+    }
+};
+
+struct UnstructuredMesh {
+    int npe = 0;            // 8 or 4
+    int64_t n_cells = 0, n_nodes = 0, n_dofs = 0;
+    int n_colors = 0;
+    std::vector<int64_t> color_ptr;  // cells of colour c are order[color_ptr[c] .. color_ptr[c+1])
+    int32_t* d_order = nullptr;      // cell ids sorted by colour
+    int32_t* d_celldofs = nullptr;   // [3*npe][n_cells] (dof-major: coalesced over cells)
+    double* d_ke = nullptr;          // [(3npe)^2][n_cells] unit-modulus element matrices
+    double* d_vol = nullptr;         // element volumes
+    // CSR filter
+    int64_t nnz = 0;
+    int64_t* d_rowptr = nullptr;
+    int32_t* d_col = nullptr;
+    double* d_w = nullptr;           // max(0, R - dist)
+    double* d_D = nullptr;           // D_i = sum_j w_ij V_j
+};
+
+struct NcclApi;  // comm.cu
+
+struct esimp_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    esimp_params prm{};
+    int64_t launches = 0;
+
+    // ---- distributed
+    int rank = 0, nranks = 1;
+    void* nccl_comm = nullptr;
+
+    // ---- mesh kind
+    bool structured = false, unstructured = false;
+    GridDev g{};
+    double hx = 1, hy = 1, hz = 1;
+    int own_p0 = 0, own_p1 = 0;  // owned local node planes
+    int own_e0 = 0, own_e1 = 0;  // owned local element layers
+    int mv_e0 = 0, mv_e1 = 0;    // element layers the operator visits (owned + redundant left layer)
+    int halo_e = 0;              // ghost element layers per interior side
+    bool has_left = false, has_right = false;
+    int64_t n_dofs_global = 0, n_cells_global = 0;
+    int64_t ndof_loc = 0, ncell_loc = 0;  // stored (incl. ghosts)
+    int64_t own_dof0 = 0, own_dof1 = 0;   // owned dof range in local storage
+    int64_t own_cell0 = 0, own_cell1 = 0; // owned cell range
+    int64_t* d_dof_of_node = nullptr;     // caller numbering (global, 3*n_nodes) or null
+    UnstructuredMesh um;
+
+    // element matrices (host copies; uploaded to __constant__ on demand)
+    double K0[24 * 24];
+    double B[8][3][3];
+    double kdiag[3];
+    bool k0_valid = false;
+    double diag_value = 1.0;  // m = mean |diag K|
+
+    // stencil filter
+    std::vector<int> st_off;   // 3*n
+    std::vector<double> st_w;
+    int st_n = 0, st_halo = 0;
+    double* d_filtD = nullptr;  // D_i per stored cell (structured)
+    bool filter_ready = false;
+
+    // ---- device state
+    uint8_t* d_mask = nullptr;  // per node (structured) / per dof (unstructured)
+    int64_t* d_fixed = nullptr; // prescribed dofs in device numbering
+    int64_t n_fixed = 0;
+    double *d_f = nullptr, *d_u = nullptr, *d_r = nullptr, *d_p = nullptr, *d_q = nullptr, *d_dinv = nullptr;
+    double *d_rho = nullptr, *d_phys = nullptr, *d_E = nullptr, *d_dc = nullptr, *d_dcf = nullptr, *d_dv = nullptr,
+           *d_rho_new = nullptr, *d_rho_old = nullptr, *d_ctmp = nullptr;
+    double* d_stage = nullptr;  // staging for global host arrays
+    int64_t stage_cap = 0;
+    // reductions
+    double* d_partial = nullptr;    // [8][RED_BLOCKS]
+    unsigned int* d_ticket = nullptr;
+    double* d_scal = nullptr;       // device scalars (see SC_* in vector_ops.cu)
+    double* h_scal = nullptr;       // pinned mirror
+    bool density_set = false, load_set = false, design_set = false;
+    double f_norm2 = 0.0;
+    cudaEvent_t ev[6]{};
+};
+
+int esimp_fail(esimp_ctx* ctx, int code, const std::string& msg);
+
+// ------------------------------------------------------------------ launch geometry helpers
+constexpr int RED_BLOCKS = 148 * 4;  // persistent grid-stride grids: 4 CTAs of 256 per SM
+constexpr int RED_THREADS = 256;
+constexpr int N_SCAL = 32;
+
+// device scalar slots
+enum {
+    SC_PQ = 0, SC_RZ0 = 1, SC_RZ1 = 2, SC_RR = 3, SC_FF = 4, SC_VOL = 5, SC_ENERGY = 6, SC_CHANGE = 7,
+    SC_GRAY = 8, SC_MAXU = 9, SC_DIAGSUM = 10, SC_TMP0 = 11, SC_TMP1 = 12, SC_TMP2 = 13
+};
+
+// ------------------------------------------------------------------ module entry points
+// hex8_structured.cu
+int hex8_upload_constants(esimp_ctx* ctx);
+int hex8_matvec(esimp_ctx* ctx, const double* d_in, double* d_out, int variant);
+int hex8_diagonal(esimp_ctx* ctx);                 // fills d_dinv with 1/diag, sets diag_value
+int hex8_sens_energy(esimp_ctx* ctx);              // d_dc (owned), SC_ENERGY
+// vector_ops.cu
+int vec_dot(esimp_ctx* ctx, const double* a, const double* b, int slot);
+int vec_fixup_dirichlet(esimp_ctx* ctx, const double* in, double* out);
+int pcg_solve(esimp_ctx* ctx, int* iters, double* relres);
+int vec_gather_to_device(esimp_ctx* ctx, const double* d_src_global, double* d_dst_local);
+int vec_scatter_from_device(esimp_ctx* ctx, const double* d_src_local, double* d_dst_global);
+int cell_gather_to_device(esimp_ctx* ctx, const double* d_src_global, double* d_dst_local);
+int cell_scatter_from_device(esimp_ctx* ctx, const double* d_src_local, double* d_dst_global);
+int reduce_sum_scaled(esimp_ctx* ctx, const double* a, const double* w_or_null, double scale, int64_t i0, int64_t i1, int slot);
+int reduce_metrics(esimp_ctx* ctx);                // change / grayness / max|u|
+int fetch_scalars(esimp_ctx* ctx);                 // d_scal -> h_scal (sync)
+int allreduce_scalars(esimp_ctx* ctx, int slot0, int n, bool is_max);
+// filter_oc.cu
+int simp_modulus(esimp_ctx* ctx);                  // d_phys -> d_E (all stored layers)
+int filter_build_stencil(esimp_ctx* ctx);
+int filter_sens_apply(esimp_ctx* ctx, const double* rho, const double* dc, double* out);
+int filter_dens_apply(esimp_ctx* ctx, const double* rho, double* out);
+int filter_densT_apply(esimp_ctx* ctx, const double* s, double* out);
+int oc_update(esimp_ctx* ctx, const double* rho, const double* dc, const double* dv, double* rho_new, double* lambda,
+              int* steps);
+// unstructured.cu
+int um_build(esimp_ctx* ctx, int celltype, int64_t n_cells, int64_t n_nodes, const double* xyz, const int64_t* conn,
+             const int64_t* celldofs);
+int um_matvec(esimp_ctx* ctx, const double* d_in, double* d_out);
+int um_diagonal(esimp_ctx* ctx);
+int um_sens_energy(esimp_ctx* ctx);
+int um_filter_build(esimp_ctx* ctx, const int64_t* rowptr, const int64_t* col, const double* centers,
+                    const double* volumes, double R);
+void um_free(esimp_ctx* ctx);
+void hex8_element_matrix(const double* xyz8, double lam, double mu, double* ke24);
+void tet4_element_matrix(const double* xyz4, double lam, double mu, double* ke12);
+// comm.cu
+int comm_unique_id(void* id128, std::string& err);
+int comm_init(esimp_ctx* ctx, int rank, int nranks, const void* id128);
+void comm_destroy(esimp_ctx* ctx);
+int comm_allreduce(esimp_ctx* ctx, double* d_buf, int n, bool is_max);
+int comm_halo_nodes(esimp_ctx* ctx, double* d_vec);            // one-plane u halo, both directions
+int comm_halo_cells(esimp_ctx* ctx, double* d_arr);            // halo_e-layer cell halo, both directions
+
+// ------------------------------------------------------------------ device reduction helpers
+#ifdef __CUDACC__
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Deterministic grid reduction of NV values: warp shuffle -> smem -> per-block partial ->
+// the last block to finish (ticket) folds the partials in a fixed order and writes out[i].
+// partial: [NV][gridDim.x]; all threads of all blocks must call it.
+template <int NV>
+struct RedOut {
+    double* p[NV];
+};
+template <int NV, bool IS_MAX>
+__device__ __forceinline__ void grid_reduce(double (&v)[NV], double* partial, unsigned int* ticket, const RedOut<NV>& out) {
+    __shared__ double s_red[NV][32];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double w = IS_MAX ? warp_max(v[i]) : warp_sum(v[i]);
+        if (lane == 0) s_red[i][warp] = w;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double w = lane < nwarp ? s_red[i][lane] : (IS_MAX ? -1.0e300 : 0.0);
+            w = IS_MAX ? warp_max(w) : warp_sum(w);
+            if (lane == 0) partial[(size_t)i * gridDim.x + blockIdx.x] = w;
+        }
+    }
+    if (threadIdx.x == 0) {
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double acc = IS_MAX ? -1.0e300 : 0.0;
+            for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
+                double w = __ldcg(&partial[(size_t)i * gridDim.x + b]);
+                acc = IS_MAX ? fmax(acc, w) : acc + w;
+            }
+            acc = IS_MAX ? warp_max(acc) : warp_sum(acc);
+            __syncthreads();
+            if (lane == 0) s_red[i][warp] = acc;
+            __syncthreads();
+            if (warp == 0) {
+                double w = lane < nwarp ? s_red[i][lane] : (IS_MAX ? -1.0e300 : 0.0);
+                w = IS_MAX ? warp_max(w) : warp_sum(w);
+                if (lane == 0) *out.p[i] = w;
+            }
+        }
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
+}
+#endif

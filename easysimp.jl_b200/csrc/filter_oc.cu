@@ -1,0 +1,274 @@
+// filter_oc.cu -- SIMP modulus, FilterCache applies (stencil on structured grids, CSR otherwise)
+// and the optimality-criteria update.
+//
+// Replaces
+//   create_simp_material_model        FiniteElementAnalysis.jl:100-112   (E = Emin + (E0-Emin) rho^p)
+//   apply_sensitivity_filter_cached!  SensitivityFilter.jl:33-67
+//   apply_density_filter_cached!      DensityFilter.jl:30-60
+//   apply_density_filter_chain_rule_cached!  DensityFilter.jl:77-117
+//   optimality_criteria_update        OptimalityCriteria.jl:69-146
+// On a structured grid the KD-tree neighbour lists of create_filter_cache (FilterCommon.jl:61-98)
+// are a fixed stencil {(di,dj,dk): |offset| <= R}; weights max(0, R - dist) sit in constant memory
+// and the truncated stencils at the domain boundary give per-cell denominators.
+#include <math.h>
+
+#include <algorithm>
+
+#include "ctx.cuh"
+
+constexpr int MAX_STENCIL = 1100;
+__constant__ int c_st_di[MAX_STENCIL], c_st_dj[MAX_STENCIL], c_st_dk[MAX_STENCIL];
+__constant__ double c_st_w[MAX_STENCIL];
+static const esimp_ctx* g_stencil_owner = nullptr;
+
+#define LAUNCH_STREAM(kern, ...)                                        \
+    do {                                                                \
+        kern<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(__VA_ARGS__); \
+        ctx->launches++;                                                \
+        ESIMP_CUDA(cudaGetLastError());                                 \
+    } while (0)
+
+// ---------------------------------------------------------------------------- modulus
+__global__ void k_modulus(const double* __restrict__ rho, double* __restrict__ E, long long n, double E0, double Emin, double p) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double r = rho[i];
+        double rp = (p == 3.0) ? r * r * r : pow(r, p);
+        E[i] = Emin + (E0 - Emin) * rp;
+    }
+}
+int simp_modulus(esimp_ctx* ctx) {
+    LAUNCH_STREAM(k_modulus, ctx->d_phys, ctx->d_E, (long long)ctx->ncell_loc, ctx->prm.E0, ctx->prm.Emin, ctx->prm.p);
+    return ESIMP_OK;
+}
+
+// ---------------------------------------------------------------------------- stencil filter
+static int upload_stencil(esimp_ctx* ctx) {
+    if (g_stencil_owner == ctx) return ESIMP_OK;
+    std::vector<int> di(ctx->st_n), dj(ctx->st_n), dk(ctx->st_n);
+    for (int s = 0; s < ctx->st_n; ++s) {
+        di[s] = ctx->st_off[3 * s];
+        dj[s] = ctx->st_off[3 * s + 1];
+        dk[s] = ctx->st_off[3 * s + 2];
+    }
+    ESIMP_CUDA(cudaMemcpyToSymbol(c_st_di, di.data(), sizeof(int) * ctx->st_n));
+    ESIMP_CUDA(cudaMemcpyToSymbol(c_st_dj, dj.data(), sizeof(int) * ctx->st_n));
+    ESIMP_CUDA(cudaMemcpyToSymbol(c_st_dk, dk.data(), sizeof(int) * ctx->st_n));
+    ESIMP_CUDA(cudaMemcpyToSymbol(c_st_w, ctx->st_w.data(), sizeof(double) * ctx->st_n));
+    g_stencil_owner = ctx;
+    return ESIMP_OK;
+}
+
+// D_i = sum_j w_ij V_j over the in-domain stencil (denominator of the density filter); computed for
+// every stored cell (ghost layers too) from GLOBAL grid bounds, so it needs no halo.
+__global__ void k_filter_D(GridDev g, int nst, double vol, double* __restrict__ D, long long n) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        int k = (int)(e % g.nz);
+        long long t = e / g.nz;
+        int j = (int)(t % g.ny);
+        int gi = g.ge0 + (int)(t / g.ny);
+        double den = 0.0;
+        for (int s = 0; s < nst; ++s) {
+            int ii = gi + c_st_di[s], jj = j + c_st_dj[s], kk = k + c_st_dk[s];
+            if (ii < 0 || ii >= g.nx || jj < 0 || jj >= g.ny || kk < 0 || kk >= g.nz) continue;
+            den += c_st_w[s] * vol;
+        }
+        D[e] = den;
+    }
+}
+
+int filter_build_stencil(esimp_ctx* ctx) {
+    const double R = ctx->prm.filter_radius;
+    const int ri = (int)floor(R / ctx->hx + 1e-9), rj = (int)floor(R / ctx->hy + 1e-9), rk = (int)floor(R / ctx->hz + 1e-9);
+    ctx->st_off.clear();
+    ctx->st_w.clear();
+    // neighbour order: ascending caller cell id (x fastest) like the sorted lists of the oracle
+    for (int dk = -rk; dk <= rk; ++dk)
+        for (int dj = -rj; dj <= rj; ++dj)
+            for (int di = -ri; di <= ri; ++di) {
+                double dx = di * ctx->hx, dy = dj * ctx->hy, dz = dk * ctx->hz;
+                double w = R - sqrt(dx * dx + dy * dy + dz * dz);
+                if (w > 0.0) {  // weight > 0 only (SensitivityFilter.jl:52, DensityFilter.jl:48)
+                    ctx->st_off.push_back(di);
+                    ctx->st_off.push_back(dj);
+                    ctx->st_off.push_back(dk);
+                    ctx->st_w.push_back(w);
+                }
+            }
+    ctx->st_n = (int)ctx->st_w.size();
+    if (ctx->st_n > MAX_STENCIL) return esimp_fail(ctx, ESIMP_ERR_ARG, "filter radius too large for the stencil table");
+    ctx->st_halo = 0;
+    for (int s = 0; s < ctx->st_n; ++s) ctx->st_halo = std::max(ctx->st_halo, abs(ctx->st_off[3 * s]));
+    if (ctx->nranks > 1 && ctx->st_halo > ctx->halo_e)
+        return esimp_fail(ctx, ESIMP_ERR_STATE, "filter radius needs more ghost layers than the slab holds");
+    g_stencil_owner = nullptr;
+    ESIMP_TRY(upload_stencil(ctx));
+    if (!ctx->d_filtD) ESIMP_CUDA(cudaMalloc(&ctx->d_filtD, sizeof(double) * ctx->ncell_loc));
+    LAUNCH_STREAM(k_filter_D, ctx->g, ctx->st_n, ctx->hx * ctx->hy * ctx->hz, ctx->d_filtD, (long long)ctx->ncell_loc);
+    ctx->filter_ready = true;
+    return ESIMP_OK;
+}
+
+// mode 0: sensitivity filter, 1: density filter, 2: density filter transpose
+template <int MODE>
+__global__ void k_filter_stencil(GridDev g, int le0, int le1, int nst, double vol, const double* __restrict__ a,
+                                 const double* __restrict__ b, const double* __restrict__ D, double* __restrict__ out) {
+    long long n = (long long)(le1 - le0) * g.eplane;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        long long e = (long long)le0 * g.eplane + idx;
+        int k = (int)(e % g.nz);
+        long long t = e / g.nz;
+        int j = (int)(t % g.ny);
+        int le = (int)(t / g.ny);
+        int gi = g.ge0 + le;
+        double num = 0.0, den = 0.0;
+        for (int s = 0; s < nst; ++s) {
+            int di = c_st_di[s], jj = j + c_st_dj[s], kk = k + c_st_dk[s];
+            int ii = gi + di;
+            if (ii < 0 || ii >= g.nx || jj < 0 || jj >= g.ny || kk < 0 || kk >= g.nz) continue;
+            long long nb = g.cell(le + di, jj, kk);
+            double w = c_st_w[s];
+            if (MODE == 0) {  // a = rho (design), b = dc
+                num += w * a[nb] * b[nb] / vol;
+                den += w;
+            } else if (MODE == 1) {  // a = rho
+                double wv = w * vol;
+                num += wv * a[nb];
+                den += wv;
+            } else {  // a = s ; out_e = sum_i (w_ie V_e / D_i) s_i
+                double Di = D[nb];
+                if (Di > 1e-12) num += (w * vol / Di) * a[nb];
+            }
+        }
+        double r;
+        if (MODE == 0) {
+            double rho_safe = fmax(1e-3, a[e]);
+            r = den > 1e-12 ? num / (rho_safe / vol * den) : b[e];
+        } else if (MODE == 1) {
+            r = den > 1e-12 ? num / den : a[e];
+        } else {
+            r = num;
+        }
+        out[e] = r;
+    }
+}
+
+// CSR variants (unstructured meshes)
+template <int MODE>
+__global__ void k_filter_csr(long long n, const long long* __restrict__ rowptr, const int* __restrict__ col,
+                             const double* __restrict__ w, const double* __restrict__ vol, const double* __restrict__ a,
+                             const double* __restrict__ b, const double* __restrict__ D, double* __restrict__ out) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+        double num = 0.0, den = 0.0;
+        for (long long q = rowptr[e]; q < rowptr[e + 1]; ++q) {
+            double wq = w[q];
+            if (!(wq > 0.0)) continue;
+            int nb = col[q];
+            if (MODE == 0) {
+                num += wq * a[nb] * b[nb] / vol[nb];
+                den += wq;
+            } else if (MODE == 1) {
+                double wv = wq * vol[nb];
+                num += wv * a[nb];
+                den += wv;
+            } else {  // symmetric neighbour relation: w_ie = w_ei
+                double Di = D[nb];
+                if (Di > 1e-12) num += (wq * vol[e] / Di) * a[nb];
+            }
+        }
+        double r;
+        if (MODE == 0) {
+            double rho_safe = fmax(1e-3, a[e]);
+            r = den > 1e-12 ? num / (rho_safe / vol[e] * den) : b[e];
+        } else if (MODE == 1) {
+            r = den > 1e-12 ? num / den : a[e];
+        } else {
+            r = num;
+        }
+        out[e] = r;
+    }
+}
+
+template <int MODE>
+static int filter_apply(esimp_ctx* ctx, const double* a, const double* b, double* out) {
+    if (!ctx->filter_ready) return esimp_fail(ctx, ESIMP_ERR_STATE, "filter not built");
+    if (ctx->structured) {
+        ESIMP_TRY(upload_stencil(ctx));
+        auto kern = k_filter_stencil<MODE>;
+        LAUNCH_STREAM(kern, ctx->g, ctx->own_e0, ctx->own_e1, ctx->st_n, ctx->hx * ctx->hy * ctx->hz, a, b,
+                      ctx->d_filtD, out);
+    } else {
+        const UnstructuredMesh& um = ctx->um;
+        auto kern = k_filter_csr<MODE>;
+        LAUNCH_STREAM(kern, (long long)um.n_cells, (const long long*)um.d_rowptr, um.d_col, um.d_w, um.d_vol, a, b,
+                      um.d_D, out);
+    }
+    return ESIMP_OK;
+}
+int filter_sens_apply(esimp_ctx* ctx, const double* rho, const double* dc, double* out) { return filter_apply<0>(ctx, rho, dc, out); }
+int filter_dens_apply(esimp_ctx* ctx, const double* rho, double* out) { return filter_apply<1>(ctx, rho, nullptr, out); }
+int filter_densT_apply(esimp_ctx* ctx, const double* s, double* out) { return filter_apply<2>(ctx, s, nullptr, out); }
+
+// ---------------------------------------------------------------------------- optimality criteria
+// One bisection step (OptimalityCriteria.jl:102-126): candidate for every stored cell (ghost layers
+// too, so a following density filter needs no halo exchange) and, when no density filter is active,
+// the volume sum over owned cells with a warp-shuffle reduction.
+__global__ void k_oc_candidate(const double* __restrict__ rho, const double* __restrict__ dc, const double* __restrict__ dv,
+                               const double* __restrict__ vol, double vol_uniform, double lam, double move, double damping,
+                               double* __restrict__ rn, long long n, long long o0, long long o1, double* partial,
+                               unsigned int* ticket, RedOut<1> out) {
+    double acc[1] = {0.0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double x = rho[i];
+        double Be = fabs(dc[i]) / (lam * dv[i]);
+        double cand = x * ((damping == 0.5) ? sqrt(Be) : pow(Be, damping));
+        double v = fmax(1e-3, fmax(x - move, fmin(1.0, fmin(x + move, cand))));
+        rn[i] = v;
+        if (i >= o0 && i < o1) acc[0] += v * (vol ? vol[i] : vol_uniform);
+    }
+    grid_reduce<1, false>(acc, partial, ticket, out);
+}
+
+int oc_update(esimp_ctx* ctx, const double* rho, const double* dc, const double* dv, double* rho_new, double* lambda, int* steps) {
+    const bool use_df = ctx->prm.filter_type == ESIMP_FILTER_DENSITY;
+    const double* vol = ctx->unstructured ? ctx->um.d_vol : nullptr;
+    const double vuni = ctx->hx * ctx->hy * ctx->hz;
+    // total volume and target (OptimalityCriteria.jl:84)
+    double total_volume;
+    if (ctx->unstructured) {
+        ESIMP_TRY(reduce_sum_scaled(ctx, ctx->um.d_vol, nullptr, 1.0, 0, ctx->ncell_loc, SC_TMP0));
+        ESIMP_TRY(fetch_scalars(ctx));
+        total_volume = ctx->h_scal[SC_TMP0];
+    } else {
+        total_volume = vuni * (double)ctx->n_cells_global;
+    }
+    const double target = ctx->prm.volume_fraction * total_volume;
+    double lo = 1e-9, hi = 1e9, lam = NAN;
+    int it = 0, status = ESIMP_WARN_OC_MAXIT;
+    RedOut<1> out{{ctx->d_scal + SC_VOL}};
+    for (it = 1; it <= 200; ++it) {
+        lam = 0.5 * (lo + hi);
+        LAUNCH_STREAM(k_oc_candidate, rho, dc, dv, vol, vuni, lam, ctx->prm.move_limit, ctx->prm.damping, rho_new,
+                      (long long)ctx->ncell_loc, (long long)ctx->own_cell0, (long long)ctx->own_cell1, ctx->d_partial, ctx->d_ticket,
+                      out);
+        if (use_df) {
+            ESIMP_TRY(filter_dens_apply(ctx, rho_new, ctx->d_ctmp));
+            ESIMP_TRY(reduce_sum_scaled(ctx, ctx->d_ctmp, vol, vol ? 1.0 : vuni, ctx->own_cell0, ctx->own_cell1, SC_VOL));
+        } else {
+            ESIMP_TRY(allreduce_scalars(ctx, SC_VOL, 1, false));
+        }
+        ESIMP_TRY(fetch_scalars(ctx));
+        double err = ctx->h_scal[SC_VOL] - target;
+        if (fabs(err) < 1e-6) {
+            status = ESIMP_OK;
+            break;
+        }
+        if (err > 0)
+            lo = lam;
+        else
+            hi = lam;
+    }
+    if (it > 200) it = 200;
+    if (lambda) *lambda = lam;
+    if (steps) *steps = it;
+    return status;
+}

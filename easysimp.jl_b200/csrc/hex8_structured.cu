@@ -1,0 +1,638 @@
+// hex8_structured.cu -- matrix-free hex8 operator on structured grids (sm_100a)
+//
+// Replaces, for grids made by generate_grid(Hexahedron, ...):
+//   * assemble_with_cache! (FiniteElementAnalysis.jl:678-712): K = sum_e E(rho_e)/E0 * K_unit
+//   * Ferrite apply!(K,f,ch) (Optimization.jl:581-583): zero rows/cols of prescribed dofs
+//   * the K*u products inside the solve (Optimization.jl:317) and the energy (:320)
+//   * calculate_sensitivities! (SensitivityAnalysis.jl:31-80): u_e' K0 u_e per cell
+// by y = sum_e E_e G_e' K0 G_e u applied without ever forming K.
+//
+// The fused kernel works in the trilinear *mode basis*: per displacement component the 8 nodal
+// values of a cell are transformed by a 2x2x2 Walsh-Hadamard butterfly into the coefficients of
+// {1, xi, eta, zeta, xi.eta, eta.zeta, xi.zeta, xi.eta.zeta}.  For a cuboid the reflection
+// symmetry Z2^3 makes K~ = T'K0T/64 block diagonal: 8 parity classes, one (component, mode)
+// pair per component in each class, 45 non-zeros instead of 576 (pattern below, checked on the
+// host for every (hx,hy,hz,nu)).  A thread owns one (y,z) column of cells and marches along x:
+// the 2-D transform of a node plane is shared by the two cells either side of it, and the
+// x-direction butterfly of the output is shared the same way, so a cell costs ~170 FP64 issue
+// slots instead of 600 and each u value is read from HBM once.
+#include <math.h>
+#include <string.h>
+
+#include "ctx.cuh"
+
+// ---------------------------------------------------------------------------- constants
+__constant__ double c_K0[24 * 24];  // dense unit-modulus element matrix, local dof 3a+c
+__constant__ double c_B[8][3][3];   // mode-space blocks per parity class
+__constant__ double c_kdiag[3];     // K0[3a+c,3a+c] (same for every node a of a cuboid)
+static const esimp_ctx* g_const_owner = nullptr;
+
+// structural non-zeros of the class blocks (class q = mode ^ (1<<component))
+__device__ __host__ constexpr bool pat(int q, int c, int d) {
+    // q=0,7: full; q=1,2,4: the component whose mode is the constant (translation) drops out;
+    // q=3,5,6: the component whose mode is xi.eta.zeta decouples from the other two.
+    return (q == 0 || q == 7)   ? true
+           : (q == 1)           ? (c != 0 && d != 0)
+           : (q == 2)           ? (c != 1 && d != 1)
+           : (q == 4)           ? (c != 2 && d != 2)
+           : (q == 3)           ? ((c == 2) == (d == 2))
+           : (q == 5)           ? ((c == 1) == (d == 1))
+                                : ((c == 0) == (d == 0));
+}
+
+static const double HEXREF[8][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1},
+                                    {-1, -1, 1},  {1, -1, 1},  {1, 1, 1},  {-1, 1, 1}};
+
+// Element matrix from shape-function gradients:
+// ke[(a,c),(b,d)] += dV (lam g_a[c] g_b[d] + mu (delta_cd g_a.g_b + g_a[d] g_b[c]))
+// == (sym grad N_i) : (lam tr(eps_j) I + 2 mu eps_j), FiniteElementAnalysis.jl:181-190.
+static void add_gradients(int n, const double (*g)[3], double lam, double mu, double dV, double* ke) {
+    const int nd = 3 * n;
+    for (int a = 0; a < n; ++a)
+        for (int b = 0; b < n; ++b) {
+            double gg = g[a][0] * g[b][0] + g[a][1] * g[b][1] + g[a][2] * g[b][2];
+            for (int c = 0; c < 3; ++c)
+                for (int d = 0; d < 3; ++d) {
+                    double v = lam * g[a][c] * g[b][d] + mu * g[a][d] * g[b][c] + (c == d ? mu * gg : 0.0);
+                    ke[(3 * a + c) * nd + 3 * b + d] += dV * v;
+                }
+        }
+}
+
+static double inv3(const double J[3][3], double Ji[3][3]) {
+    double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                 J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+    double id = 1.0 / det;
+    Ji[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * id;
+    Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+    Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+    Ji[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) * id;
+    Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+    Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+    Ji[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) * id;
+    Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+    Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+    return det;
+}
+
+// 8-node hexahedron, 2x2x2 Gauss (QuadratureRule{RefHexahedron}(2), FiniteElementAnalysis.jl:138)
+void hex8_element_matrix(const double* xyz, double lam, double mu, double* ke) {
+    memset(ke, 0, sizeof(double) * 24 * 24);
+    const double gp = 1.0 / sqrt(3.0);
+    for (int qz = 0; qz < 2; ++qz)
+        for (int qy = 0; qy < 2; ++qy)
+            for (int qx = 0; qx < 2; ++qx) {
+                double xi[3] = {qx ? gp : -gp, qy ? gp : -gp, qz ? gp : -gp};
+                double dN[8][3];
+                for (int a = 0; a < 8; ++a) {
+                    double f0 = 1 + HEXREF[a][0] * xi[0], f1 = 1 + HEXREF[a][1] * xi[1], f2 = 1 + HEXREF[a][2] * xi[2];
+                    dN[a][0] = 0.125 * HEXREF[a][0] * f1 * f2;
+                    dN[a][1] = 0.125 * f0 * HEXREF[a][1] * f2;
+                    dN[a][2] = 0.125 * f0 * f1 * HEXREF[a][2];
+                }
+                double J[3][3] = {{0}}, Ji[3][3];
+                for (int a = 0; a < 8; ++a)
+                    for (int c = 0; c < 3; ++c)
+                        for (int d = 0; d < 3; ++d) J[c][d] += xyz[3 * a + c] * dN[a][d];
+                double det = inv3(J, Ji);
+                double g[8][3];
+                for (int a = 0; a < 8; ++a)
+                    for (int c = 0; c < 3; ++c) g[a][c] = dN[a][0] * Ji[0][c] + dN[a][1] * Ji[1][c] + dN[a][2] * Ji[2][c];
+                add_gradients(8, g, lam, mu, fabs(det), ke);
+            }
+}
+
+// 4-node tetrahedron: constant gradients, K = V B'DB (weights of any rule sum to 1/6)
+void tet4_element_matrix(const double* xyz, double lam, double mu, double* ke) {
+    memset(ke, 0, sizeof(double) * 12 * 12);
+    const double dN[4][3] = {{-1, -1, -1}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    double J[3][3] = {{0}}, Ji[3][3];
+    for (int a = 0; a < 4; ++a)
+        for (int c = 0; c < 3; ++c)
+            for (int d = 0; d < 3; ++d) J[c][d] += xyz[3 * a + c] * dN[a][d];
+    double det = inv3(J, Ji);
+    double g[4][3];
+    for (int a = 0; a < 4; ++a)
+        for (int c = 0; c < 3; ++c) g[a][c] = dN[a][0] * Ji[0][c] + dN[a][1] * Ji[1][c] + dN[a][2] * Ji[2][c];
+    add_gradients(4, g, lam, mu, fabs(det) / 6.0, ke);
+}
+
+// Build K0 (unit modulus), its mode-space blocks and the nodal diagonal for the context's cuboid.
+int hex8_upload_constants(esimp_ctx* ctx) {
+    if (!ctx->k0_valid) {
+        const double nu = ctx->prm.nu;
+        const double lam = nu / ((1 + nu) * (1 - 2 * nu)), mu = 1.0 / (2 * (1 + nu));  // SensitivityAnalysis.jl:44-45
+        double xyz[24];
+        for (int a = 0; a < 8; ++a) {
+            xyz[3 * a + 0] = 0.5 * (1 + HEXREF[a][0]) * ctx->hx;
+            xyz[3 * a + 1] = 0.5 * (1 + HEXREF[a][1]) * ctx->hy;
+            xyz[3 * a + 2] = 0.5 * (1 + HEXREF[a][2]) * ctx->hz;
+        }
+        hex8_element_matrix(xyz, lam, mu, ctx->K0);
+        // K~ = T' K0 T / 64 with T[3a+c][3m+c] = sx^bx sy^by sz^bz, m = bx + 2 by + 4 bz
+        double H[8][8];
+        for (int a = 0; a < 8; ++a)
+            for (int m = 0; m < 8; ++m)
+                H[a][m] = ((m & 1) ? HEXREF[a][0] : 1.0) * ((m & 2) ? HEXREF[a][1] : 1.0) * ((m & 4) ? HEXREF[a][2] : 1.0);
+        static double Kt[24][24];
+        double kmax = 0;
+        for (int m1 = 0; m1 < 8; ++m1)
+            for (int c = 0; c < 3; ++c)
+                for (int m2 = 0; m2 < 8; ++m2)
+                    for (int d = 0; d < 3; ++d) {
+                        double s = 0;
+                        for (int a = 0; a < 8; ++a)
+                            for (int b = 0; b < 8; ++b) s += H[a][m1] * ctx->K0[(3 * a + c) * 24 + 3 * b + d] * H[b][m2];
+                        Kt[3 * m1 + c][3 * m2 + d] = s / 64.0;
+                        kmax = fmax(kmax, fabs(s / 64.0));
+                    }
+        for (int i = 0; i < 24; ++i)
+            for (int j = 0; j < 24; ++j) {
+                int m1 = i / 3, c = i % 3, m2 = j / 3, d = j % 3;
+                int q1 = m1 ^ (1 << c), q2 = m2 ^ (1 << d);
+                bool structural = (q1 == q2) && pat(q1, c, d);
+                if (!structural && fabs(Kt[i][j]) > 1e-12 * kmax)
+                    return esimp_fail(ctx, ESIMP_ERR_STATE, "mode-space K0 violates the cuboid parity pattern");
+            }
+        for (int q = 0; q < 8; ++q)
+            for (int c = 0; c < 3; ++c)
+                for (int d = 0; d < 3; ++d) ctx->B[q][c][d] = pat(q, c, d) ? Kt[3 * (q ^ (1 << c)) + c][3 * (q ^ (1 << d)) + d] : 0.0;
+        for (int c = 0; c < 3; ++c) ctx->kdiag[c] = ctx->K0[c * 24 + c];
+        ctx->k0_valid = true;
+        g_const_owner = nullptr;
+    }
+    if (g_const_owner != ctx) {
+        ESIMP_CUDA(cudaMemcpyToSymbolAsync(c_K0, ctx->K0, sizeof(ctx->K0), 0, cudaMemcpyHostToDevice, ctx->stream));
+        ESIMP_CUDA(cudaMemcpyToSymbolAsync(c_B, ctx->B, sizeof(ctx->B), 0, cudaMemcpyHostToDevice, ctx->stream));
+        ESIMP_CUDA(cudaMemcpyToSymbolAsync(c_kdiag, ctx->kdiag, sizeof(ctx->kdiag), 0, cudaMemcpyHostToDevice, ctx->stream));
+        g_const_owner = ctx;
+    }
+    return ESIMP_OK;
+}
+
+// ---------------------------------------------------------------------------- butterflies
+// forward 2-D transform of the 4 corner values of a (y,z) cell face:
+// F[by + 2 bz] = sum_{sy,sz} sy^by sz^bz u(sy,sz);  uYZ: first index = y offset, second = z offset
+__device__ __forceinline__ void fwd2d(double u00, double u10, double u01, double u11, double (&F)[4]) {
+    double a0 = u10 + u00, a1 = u10 - u00, b0 = u11 + u01, b1 = u11 - u01;
+    F[0] = b0 + a0;
+    F[1] = b1 + a1;
+    F[2] = b0 - a0;
+    F[3] = b1 - a1;
+}
+// inverse: y(sy,sz) = sum_b sy^by sz^bz A[b]
+__device__ __forceinline__ void inv2d(const double (&A)[4], double& y00, double& y10, double& y01, double& y11) {
+    double pm0 = A[0] - A[2], pm1 = A[1] - A[3], pp0 = A[0] + A[2], pp1 = A[1] + A[3];
+    y00 = pm0 - pm1;
+    y10 = pm0 + pm1;
+    y01 = pp0 - pp1;
+    y11 = pp0 + pp1;
+}
+
+// w = K~ v for one cell; v, w indexed [c][m], m = bx + 2 (by + 2 bz)
+__device__ __forceinline__ void apply_blocks(const double (&v)[3][8], double (&w)[3][8]) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double acc = 0.0;
+            bool first = true;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                if (pat(q, c, d)) {
+                    if (first) {
+                        acc = c_B[q][c][d] * v[d][q ^ (1 << d)];
+                        first = false;
+                    } else {
+                        acc = fma(c_B[q][c][d], v[d][q ^ (1 << d)], acc);
+                    }
+                }
+            }
+            w[c][q ^ (1 << c)] = acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------- V1: dense + atomics
+// One thread per cell, dense 24x24 from constant memory, atomicAdd into a zeroed y.
+// Debug / cross-check variant (ESIMP_MATVEC_DENSE_ATOMIC); ~3.5x the FP64 work of the fused kernel.
+__global__ void __launch_bounds__(128) k_matvec_dense_atomic(GridDev g, int le0, int le1, const double* __restrict__ E,
+                                                           const uint8_t* __restrict__ mask,
+                                                           const double* __restrict__ u, double* __restrict__ y) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long n = (long long)(le1 - le0) * g.eplane;
+    if (idx >= n) return;
+    int le = le0 + (int)(idx / g.eplane);
+    int rem = (int)(idx % g.eplane);
+    int j = rem / g.nz, k = rem % g.nz;
+    const int sx[8] = {0, 1, 1, 0, 0, 1, 1, 0}, sy[8] = {0, 0, 1, 1, 0, 0, 1, 1}, sz[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+    double ue[24];
+    long long di[8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        int lp = le + g.e2p + sx[a];
+        di[a] = g.dof(lp, 0, j + sy[a], k + sz[a]);
+        uint8_t m = mask[g.node(lp, j + sy[a], k + sz[a])];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ue[3 * a + c] = ((m >> c) & 1) ? 0.0 : u[di[a] + c * g.plane];
+    }
+    double Ee = E[g.cell(le, j, k)];
+#pragma unroll 1
+    for (int r = 0; r < 24; ++r) {
+        double acc = 0.0;
+#pragma unroll
+        for (int cidx = 0; cidx < 24; ++cidx) acc = fma(c_K0[r * 24 + cidx], ue[cidx], acc);
+        atomicAdd(&y[di[r / 3] + (r % 3) * g.plane], Ee * acc);
+    }
+}
+
+// ---------------------------------------------------------------------------- V2: fused x-march
+// Block = TZ lanes (z, fastest axis) x TY warps-rows (y).  Thread (ty,tz) owns the cell column
+// (Y0+ty, Z0+tz) and marches along x through [Lstart, Lend).  Per step it
+//   1. reads the 4 nodes of the new plane from the shared input tile (3 comps) -> Fn (12 values)
+//   2. v = E (Fn +- Fp)  (E folded into the x butterfly), w = K~ v  (45 FMAs, constant operands)
+//   3. Gp = w0 + w1 -> next plane, Gm = w0 - w1 -> this plane; A = Gp(previous cell) + Gm
+//   4. inverse 2-D butterfly -> 4 corner contributions; corner (0,0) stays in registers, the other
+//      three go through shared memory to the threads that own those nodes
+//   5. one __syncthreads per plane; node totals are stored (owner tiles) or red.add'ed (atomic tiles)
+// ATOMIC=false: tiles overlap by one cell row/column, a tile owns the nodes interior to it and the
+//   perimeter cells are computed twice: deterministic, no zero-fill, ~(1-1/TY)(1-1/TZ) efficient.
+// ATOMIC=true : tiles do not overlap; perimeter nodes are combined with atomicAdd into a y whose
+//   perimeter rows/columns were zeroed first.
+template <int TY, int TZ>
+struct FusedSmem {
+    double in[2][3][TY + 1][TZ + 1];  // masked u of a node plane, double buffered
+    double out[2][3][3][TY][TZ];      // corner contributions c01, c10, c11, double buffered
+};
+
+template <int TY, int TZ, bool ATOMIC>
+__global__ void __launch_bounds__(TY* TZ) k_matvec_fused(GridDev g, int le0, int le1, int ps0, int ps1, int chunk,
+                                                         const double* __restrict__ E, const uint8_t* __restrict__ mask,
+                                                         const double* __restrict__ u, double* __restrict__ y) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FusedSmem<TY, TZ>& sm = *reinterpret_cast<FusedSmem<TY, TZ>*>(smem_raw);
+    const int tz = threadIdx.x % TZ, ty = threadIdx.x / TZ;
+    const int tid = threadIdx.x;
+    constexpr int SY = ATOMIC ? TY : TY - 1, SZ = ATOMIC ? TZ : TZ - 1;
+    const int Y0 = blockIdx.y * SY - (ATOMIC ? 0 : 1), Z0 = blockIdx.x * SZ - (ATOMIC ? 0 : 1);
+    const int ey = Y0 + ty, ez = Z0 + tz;  // my cell column == my node (low corner)
+    const bool cell_ok = ey >= 0 && ey < g.ny && ez >= 0 && ez < g.nz;
+    const bool node_ok = ey >= 0 && ey <= g.ny && ez >= 0 && ez <= g.nz;
+    // halo node of the input tile handled by this thread (row TY, column TZ)
+    int hj = -1, hk = -1;
+    if (tid <= TZ) {
+        hj = TY;
+        hk = tid;
+    } else if (tid < TZ + 1 + TY) {
+        hj = tid - TZ - 1;
+        hk = TZ;
+    }
+    const int hy = Y0 + hj, hz = Z0 + hk;
+    const bool halo_ok = hj >= 0 && hy >= 0 && hy <= g.ny && hz >= 0 && hz <= g.nz;
+
+    // node planes this block owns and the cell layers that touch them
+    const int P0 = ps0 + blockIdx.z * chunk, P1 = min(P0 + chunk, ps1);
+    const int Lstart = max(P0 - g.e2p - 1, le0), Lend = min(P1 - g.e2p, le1);
+    if (Lstart >= Lend) return;
+    const int nsteps = Lend - Lstart;
+    const int pl0 = Lstart + g.e2p;  // first node plane read
+
+    const long long noff = (long long)ey * (g.nz + 1) + ez;       // node offset within a plane
+    const long long hoff = (long long)hy * (g.nz + 1) + hz;
+    const long long coff = (long long)ey * g.nz + ez;              // cell offset within a layer
+
+    double un[3], uh[3];
+    auto load_plane = [&](int lp) {
+        if (node_ok) {
+            uint8_t m = mask[(long long)lp * g.plane + noff];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                double v = u[(long long)(lp * 3 + c) * g.plane + noff];
+                un[c] = ((m >> c) & 1) ? 0.0 : v;
+            }
+        } else {
+            un[0] = un[1] = un[2] = 0.0;
+        }
+        if (hj >= 0) {
+            if (halo_ok) {
+                uint8_t m = mask[(long long)lp * g.plane + hoff];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    double v = u[(long long)(lp * 3 + c) * g.plane + hoff];
+                    uh[c] = ((m >> c) & 1) ? 0.0 : v;
+                }
+            } else {
+                uh[0] = uh[1] = uh[2] = 0.0;
+            }
+        }
+    };
+    auto stage_plane = [&](int buf) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) sm.in[buf][c][ty][tz] = un[c];
+        if (hj >= 0) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) sm.in[buf][c][hj][hk] = uh[c];
+        }
+    };
+    auto face_modes = [&](int buf, double (&F)[3][4]) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            fwd2d(sm.in[buf][c][ty][tz], sm.in[buf][c][ty + 1][tz], sm.in[buf][c][ty][tz + 1], sm.in[buf][c][ty + 1][tz + 1], F[c]);
+    };
+    // combine the corner contributions of plane `lp` and write the node totals
+    auto flush_plane = [&](int buf, int lp, const double (&c00)[3]) {
+        const bool store = lp >= P0 && lp < P1;
+        if (!store) return;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double s = c00[c];
+            if (tz >= 1) s += sm.out[buf][0][c][ty][tz - 1];
+            if (ty >= 1) s += sm.out[buf][1][c][ty - 1][tz];
+            if (ty >= 1 && tz >= 1) s += sm.out[buf][2][c][ty - 1][tz - 1];
+            if (node_ok) {
+                double* dst = &y[(long long)(lp * 3 + c) * g.plane + noff];
+                if (ty >= 1 && tz >= 1) {
+                    *dst = s;
+                } else if (ATOMIC) {
+                    atomicAdd(dst, s);
+                }
+            }
+            if (ATOMIC && hj >= 0 && halo_ok) {
+                double h = 0.0;
+                if (hj == TY) {  // top row: cells (TY-1, hk) and (TY-1, hk-1)
+                    if (hk < TZ) h += sm.out[buf][1][c][TY - 1][hk];
+                    if (hk >= 1) h += sm.out[buf][2][c][TY - 1][hk - 1];
+                } else {  // right column: cells (hj, TZ-1) and (hj-1, TZ-1)
+                    h += sm.out[buf][0][c][hj][TZ - 1];
+                    if (hj >= 1) h += sm.out[buf][2][c][hj - 1][TZ - 1];
+                }
+                atomicAdd(&y[(long long)(lp * 3 + c) * g.plane + hoff], h);
+            }
+        }
+    };
+
+    // ---- prologue: planes pl0 and pl0+1 into the two input buffers
+    load_plane(pl0);
+    stage_plane(0);
+    load_plane(pl0 + 1);
+    stage_plane(1);
+    double Enext = cell_ok ? E[(long long)Lstart * g.eplane + coff] : 0.0;
+    __syncthreads();
+    double Fp[3][4], Gpp[3][4];
+    face_modes(0, Fp);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) Gpp[c][b] = 0.0;
+    if (nsteps > 1) load_plane(pl0 + 2);
+    __syncthreads();  // in[0] is re-staged in step 0: every thread must have read it
+
+#pragma unroll 1
+    for (int it = 0; it < nsteps; ++it) {
+        const double Ee = Enext;
+        if (it + 1 < nsteps && cell_ok) Enext = E[(long long)(Lstart + it + 1) * g.eplane + coff];
+        double Fn[3][4];
+        face_modes((it + 1) & 1, Fn);
+        // x butterfly with the modulus folded in: v0 = E (Fn + Fp), v1 = E (Fn - Fp)
+        double v[3][8], w[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                double ep = Ee * Fp[c][b];
+                v[c][2 * b] = fma(Ee, Fn[c][b], ep);
+                v[c][2 * b + 1] = fma(Ee, Fn[c][b], -ep);
+            }
+        apply_blocks(v, w);
+        double c00[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double A[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                A[b] = Gpp[c][b] + (w[c][2 * b] - w[c][2 * b + 1]);
+                Gpp[c][b] = w[c][2 * b] + w[c][2 * b + 1];
+                Fp[c][b] = Fn[c][b];
+            }
+            double y10, y01, y11;
+            inv2d(A, c00[c], y10, y01, y11);
+            sm.out[it & 1][0][c][ty][tz] = y01;  // -> node (ty, tz+1)
+            sm.out[it & 1][1][c][ty][tz] = y10;  // -> node (ty+1, tz)
+            sm.out[it & 1][2][c][ty][tz] = y11;  // -> node (ty+1, tz+1)
+        }
+        if (it + 1 < nsteps) stage_plane(it & 1);  // plane pl0+it+2, prefetched last step
+        __syncthreads();
+        flush_plane(it & 1, pl0 + it, c00);
+        if (it + 2 < nsteps) load_plane(pl0 + it + 3);
+    }
+    // ---- epilogue: the last plane only receives Gp of the last cell
+    {
+        double c00[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double y10, y01, y11;
+            inv2d(Gpp[c], c00[c], y10, y01, y11);
+            sm.out[nsteps & 1][0][c][ty][tz] = y01;
+            sm.out[nsteps & 1][1][c][ty][tz] = y10;
+            sm.out[nsteps & 1][2][c][ty][tz] = y11;
+        }
+        __syncthreads();
+        flush_plane(nsteps & 1, pl0 + nsteps, c00);
+    }
+}
+
+// zero the tile-perimeter rows / columns of y that the ATOMIC variant accumulates into
+template <int TY, int TZ>
+__global__ void k_zero_perimeter(GridDev g, int ps0, int ps1, double* __restrict__ y) {
+    long long n = (long long)(ps1 - ps0) * 3 * g.plane;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int k = (int)(i % (g.nz + 1));
+        int j = (int)((i / (g.nz + 1)) % (g.ny + 1));
+        if ((j % TY) == 0 || (k % TZ) == 0) y[(long long)ps0 * 3 * g.plane + i] = 0.0;
+    }
+}
+
+template <int TY, int TZ, bool ATOMIC>
+static int launch_fused(esimp_ctx* ctx, const double* d_in, double* d_out) {
+    const GridDev& g = ctx->g;
+    constexpr int SY = ATOMIC ? TY : TY - 1, SZ = ATOMIC ? TZ : TZ - 1;
+    const int nty = ATOMIC ? (g.ny + SY - 1) / SY : (g.ny + 1 + SY - 1) / SY;
+    const int ntz = ATOMIC ? (g.nz + SZ - 1) / SZ : (g.nz + 1 + SZ - 1) / SZ;
+    const int nplanes = ctx->own_p1 - ctx->own_p0;
+    // x chunks: enough blocks for >= ~6 waves of 148 SMs x 2 CTAs, chunk >= 8 planes
+    int chunk = nplanes;
+    const long long tiles = (long long)nty * ntz;
+    while (chunk > 8 && tiles * ((nplanes + chunk - 1) / chunk) < 148LL * 2 * 6) chunk = (chunk + 1) / 2;
+    const int nchunk = (nplanes + chunk - 1) / chunk;
+    const size_t smem = sizeof(FusedSmem<TY, TZ>);
+    static bool attr_set = false;
+    auto kern = k_matvec_fused<TY, TZ, ATOMIC>;
+    if (!attr_set) {
+        ESIMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    if (ATOMIC) {
+        k_zero_perimeter<TY, TZ><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(g, ctx->own_p0, ctx->own_p1, d_out);
+        ctx->launches++;
+    }
+    dim3 grid(ntz, nty, nchunk), block(TY * TZ);
+    kern<<<grid, block, smem, ctx->stream>>>(g, ctx->mv_e0, ctx->mv_e1, ctx->own_p0, ctx->own_p1, chunk, ctx->d_E, ctx->d_mask,
+                                             d_in, d_out);
+    ctx->launches++;
+    ESIMP_CUDA(cudaGetLastError());
+    return ESIMP_OK;
+}
+
+// y = P K P u (prescribed rows are fixed up by vec_fixup_dirichlet)
+int hex8_matvec(esimp_ctx* ctx, const double* d_in, double* d_out, int variant) {
+    ESIMP_TRY(hex8_upload_constants(ctx));
+    const GridDev& g = ctx->g;
+    if (variant == ESIMP_MATVEC_AUTO) variant = ESIMP_MATVEC_FUSED;
+    if (variant == ESIMP_MATVEC_DENSE_ATOMIC) {
+        ESIMP_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * ctx->ndof_loc, ctx->stream));
+        long long n = (long long)(ctx->mv_e1 - ctx->mv_e0) * g.eplane;
+        k_matvec_dense_atomic<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(g, ctx->mv_e0, ctx->mv_e1, ctx->d_E,
+                                                                                      ctx->d_mask, d_in, d_out);
+        ctx->launches++;
+        ESIMP_CUDA(cudaGetLastError());
+        return ESIMP_OK;
+    }
+    if (variant == ESIMP_MATVEC_FUSED_ATOMIC) return launch_fused<8, 32, true>(ctx, d_in, d_out);
+    if (variant == ESIMP_MATVEC_FUSED_8x32) return launch_fused<8, 32, false>(ctx, d_in, d_out);
+    // owner-computes tiles: 16x16 wastes less on the perimeter than 8x32
+    return launch_fused<16, 16, false>(ctx, d_in, d_out);
+}
+
+// ---------------------------------------------------------------------------- Jacobi diagonal
+// diag(K)[node,c] = K0cc[c] * sum of E over the <=8 cells around the node; prescribed dofs get
+// diag_value (apply! puts m = mean|diag K| there).  Pass 1 accumulates sum(diag) for m.
+__global__ void k_diag(GridDev g, int ps0, int ps1, int NEX, const double* __restrict__ E, double* __restrict__ diag,
+                       double* partial, unsigned int* ticket, RedOut<1> out) {
+    long long n = (long long)(ps1 - ps0) * g.plane;
+    double acc[1] = {0.0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        int k = (int)(i % (g.nz + 1));
+        int j = (int)((i / (g.nz + 1)) % (g.ny + 1));
+        int lp = ps0 + (int)(i / g.plane);
+        double s = 0.0;
+#pragma unroll
+        for (int dx = -1; dx <= 0; ++dx) {
+            int le = lp - g.e2p + dx;
+            int ge = g.ge0 + le;
+            if (le < 0 || le >= NEX || ge < 0 || ge >= g.nx) continue;
+#pragma unroll
+            for (int dy = -1; dy <= 0; ++dy) {
+                int jj = j + dy;
+                if (jj < 0 || jj >= g.ny) continue;
+#pragma unroll
+                for (int dz = -1; dz <= 0; ++dz) {
+                    int kk = k + dz;
+                    if (kk < 0 || kk >= g.nz) continue;
+                    s += E[g.cell(le, jj, kk)];
+                }
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double d = c_kdiag[c] * s;
+            diag[g.dof(lp, c, j, k)] = d;
+            acc[0] += d;
+        }
+    }
+    grid_reduce<1, false>(acc, partial, ticket, out);
+}
+
+__global__ void k_diag_invert(GridDev g, int ps0, int ps1, const uint8_t* __restrict__ mask, double m,
+                              double* __restrict__ dinv) {
+    long long n = (long long)(ps1 - ps0) * 3 * g.plane;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        long long d = (long long)ps0 * 3 * g.plane + i;
+        int lp = (int)(d / (3 * g.plane));
+        int c = (int)((d / g.plane) % 3);
+        long long nn = (long long)lp * g.plane + d % g.plane;
+        bool fixed = (mask[nn] >> c) & 1;
+        dinv[d] = fixed ? 1.0 / m : 1.0 / dinv[d];
+    }
+}
+
+int hex8_diagonal(esimp_ctx* ctx) {
+    ESIMP_TRY(hex8_upload_constants(ctx));
+    RedOut<1> out{{ctx->d_scal + SC_DIAGSUM}};
+    k_diag<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(ctx->g, ctx->own_p0, ctx->own_p1, ctx->g.NEX, ctx->d_E, ctx->d_dinv,
+                                                        ctx->d_partial, ctx->d_ticket, out);
+    ctx->launches++;
+    ESIMP_CUDA(cudaGetLastError());
+    ESIMP_TRY(allreduce_scalars(ctx, SC_DIAGSUM, 1, false));
+    ESIMP_TRY(fetch_scalars(ctx));
+    ctx->diag_value = ctx->h_scal[SC_DIAGSUM] / (double)ctx->n_dofs_global;  // mean |diag K| (all entries > 0)
+    k_diag_invert<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(ctx->g, ctx->own_p0, ctx->own_p1, ctx->d_mask, ctx->diag_value,
+                                                               ctx->d_dinv);
+    ctx->launches++;
+    ESIMP_CUDA(cudaGetLastError());
+    return ESIMP_OK;
+}
+
+// ---------------------------------------------------------------------------- sensitivities + energy
+// One thread per owned cell: q_e = u_e' K0 u_e = v' K~ v in mode space (45 products),
+// dc_e = -p rho^(p-1) (E0-Emin) q_e (SensitivityAnalysis.jl:74-78), energy += 0.5 E_e q_e.
+// u is used as is (the reference does not mask it; after a solve u = 0 on prescribed dofs).
+__global__ void __launch_bounds__(256) k_sens_energy(GridDev g, int le0, int le1, const double* __restrict__ u,
+                                                     const double* __restrict__ rho,
+                                                     const double* __restrict__ E, double pexp, double dE,
+                                                     double* __restrict__ dc, double* partial, unsigned int* ticket,
+                                                     RedOut<1> out) {
+    long long n = (long long)(le1 - le0) * g.eplane;
+    double acc[1] = {0.0};
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
+        int le = le0 + (int)(idx / g.eplane);
+        int rem = (int)(idx % g.eplane);
+        int j = rem / g.nz, k = rem % g.nz;
+        int lp = le + g.e2p;
+        double v[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double F[2][4];
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+                double uu[2][2];
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int b = 0; b < 2; ++b) {
+                        uu[a][b] = u[g.dof(lp + s, c, j + a, k + b)];
+                    }
+                fwd2d(uu[0][0], uu[1][0], uu[0][1], uu[1][1], F[s]);
+            }
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                v[c][2 * b] = F[1][b] + F[0][b];
+                v[c][2 * b + 1] = F[1][b] - F[0][b];
+            }
+        }
+        double w[3][8];
+        apply_blocks(v, w);
+        double q = 0.0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int m = 0; m < 8; ++m)
+                if (!(m == 0)) q = fma(v[c][m], w[c][m], q);
+        long long e = g.cell(le, j, k);
+        double r = rho[e];
+        double rpow = (pexp == 3.0) ? r * r : pow(r, pexp - 1.0);
+        dc[e] = -(pexp * rpow * dE) * q;
+        acc[0] += 0.5 * E[e] * q;
+    }
+    grid_reduce<1, false>(acc, partial, ticket, out);
+}
+
+int hex8_sens_energy(esimp_ctx* ctx) {
+    ESIMP_TRY(hex8_upload_constants(ctx));
+    RedOut<1> out{{ctx->d_scal + SC_ENERGY}};
+    k_sens_energy<<<RED_BLOCKS, 256, 0, ctx->stream>>>(ctx->g, ctx->own_e0, ctx->own_e1, ctx->d_u, ctx->d_phys,
+                                                       ctx->d_E, ctx->prm.p, ctx->prm.E0 - ctx->prm.Emin, ctx->d_dc,
+                                                       ctx->d_partial, ctx->d_ticket, out);
+    ctx->launches++;
+    ESIMP_CUDA(cudaGetLastError());
+    return allreduce_scalars(ctx, SC_ENERGY, 1, false);
+}

@@ -1,0 +1,290 @@
+// vector_ops.cu -- FP64 Jacobi-PCG and the streaming vector kernels around the operator
+//
+// Replaces `u .= cholesky(Symmetric(K, :L)) \ f` (Optimization.jl:317, :532).  All PCG scalars
+// (alpha, beta, <p,q>, <r,z>, <r,r>) live on the device; the host only reads ||r||^2 back every
+// `pcg_check_every` iterations, so an iteration is 4 launches and no host synchronisation:
+//   matvec(p -> q) | dot(p,q) | update(x += a p, r -= a q, <r,Dinv r>, <r,r>) | direction(p = Dinv r + b p)
+// Every kernel is a grid-stride stream over the rank's OWNED dof range (contiguous in the
+// [plane][comp][y][z] layout); reductions are two-stage and deterministic (ctx.cuh:grid_reduce).
+#include <math.h>
+
+#include "ctx.cuh"
+
+int esimp_fail(esimp_ctx* ctx, int code, const std::string& msg);
+
+// ---------------------------------------------------------------------------- numbering maps
+// device dof index -> caller dof index (structured grids)
+__device__ __forceinline__ long long caller_dof(const GridDev& g, const long long* __restrict__ dof_of_node, long long d) {
+    int k = (int)(d % (g.nz + 1));
+    long long t = d / (g.nz + 1);
+    int j = (int)(t % (g.ny + 1));
+    t /= (g.ny + 1);
+    int c = (int)(t % 3);
+    int lp = (int)(t / 3);
+    long long nref = (long long)(g.gp0 + lp) + (long long)(g.nx + 1) * (j + (long long)(g.ny + 1) * k);
+    return dof_of_node ? dof_of_node[3 * nref + c] : 3 * nref + c;
+}
+__device__ __forceinline__ long long caller_cell(const GridDev& g, long long e) {
+    int k = (int)(e % g.nz);
+    long long t = e / g.nz;
+    int j = (int)(t % g.ny);
+    int le = (int)(t / g.ny);
+    return (long long)(g.ge0 + le) + (long long)g.nx * (j + (long long)g.ny * k);
+}
+
+__global__ void k_gather_dofs(GridDev g, const long long* __restrict__ map, const double* __restrict__ src,
+                              double* __restrict__ dst, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = src[caller_dof(g, map, i)];
+}
+__global__ void k_scatter_dofs(GridDev g, const long long* __restrict__ map, const double* __restrict__ src,
+                               double* __restrict__ dst, long long i0, long long i1) {
+    for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (long long)gridDim.x * blockDim.x)
+        dst[caller_dof(g, map, i)] = src[i];
+}
+__global__ void k_gather_cells(GridDev g, const double* __restrict__ src, double* __restrict__ dst, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        dst[i] = src[caller_cell(g, i)];
+}
+__global__ void k_scatter_cells(GridDev g, const double* __restrict__ src, double* __restrict__ dst, long long i0, long long i1) {
+    for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (long long)gridDim.x * blockDim.x)
+        dst[caller_cell(g, i)] = src[i];
+}
+
+#define LAUNCH_STREAM(kern, ...)                                            \
+    do {                                                                    \
+        kern<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(__VA_ARGS__);     \
+        ctx->launches++;                                                    \
+        ESIMP_CUDA(cudaGetLastError());                                     \
+    } while (0)
+
+int vec_gather_to_device(esimp_ctx* ctx, const double* d_src_global, double* d_dst_local) {
+    if (ctx->unstructured) {
+        ESIMP_CUDA(cudaMemcpyAsync(d_dst_local, d_src_global, sizeof(double) * ctx->ndof_loc, cudaMemcpyDeviceToDevice, ctx->stream));
+        return ESIMP_OK;
+    }
+    LAUNCH_STREAM(k_gather_dofs, ctx->g, (const long long*)ctx->d_dof_of_node, d_src_global, d_dst_local, ctx->ndof_loc);
+    return ESIMP_OK;
+}
+int vec_scatter_from_device(esimp_ctx* ctx, const double* d_src_local, double* d_dst_global) {
+    if (ctx->unstructured) {
+        ESIMP_CUDA(cudaMemcpyAsync(d_dst_global, d_src_local, sizeof(double) * ctx->ndof_loc, cudaMemcpyDeviceToDevice, ctx->stream));
+        return ESIMP_OK;
+    }
+    LAUNCH_STREAM(k_scatter_dofs, ctx->g, (const long long*)ctx->d_dof_of_node, d_src_local, d_dst_global, ctx->own_dof0, ctx->own_dof1);
+    return ESIMP_OK;
+}
+int cell_gather_to_device(esimp_ctx* ctx, const double* d_src_global, double* d_dst_local) {
+    if (ctx->unstructured) {
+        ESIMP_CUDA(cudaMemcpyAsync(d_dst_local, d_src_global, sizeof(double) * ctx->ncell_loc, cudaMemcpyDeviceToDevice, ctx->stream));
+        return ESIMP_OK;
+    }
+    LAUNCH_STREAM(k_gather_cells, ctx->g, d_src_global, d_dst_local, ctx->ncell_loc);
+    return ESIMP_OK;
+}
+int cell_scatter_from_device(esimp_ctx* ctx, const double* d_src_local, double* d_dst_global) {
+    if (ctx->unstructured) {
+        ESIMP_CUDA(cudaMemcpyAsync(d_dst_global, d_src_local, sizeof(double) * ctx->ncell_loc, cudaMemcpyDeviceToDevice, ctx->stream));
+        return ESIMP_OK;
+    }
+    LAUNCH_STREAM(k_scatter_cells, ctx->g, d_src_local, d_dst_global, ctx->own_cell0, ctx->own_cell1);
+    return ESIMP_OK;
+}
+
+// ---------------------------------------------------------------------------- scalars
+int fetch_scalars(esimp_ctx* ctx) {
+    ESIMP_CUDA(cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double) * N_SCAL, cudaMemcpyDeviceToHost, ctx->stream));
+    ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ESIMP_OK;
+}
+int allreduce_scalars(esimp_ctx* ctx, int slot0, int n, bool is_max) {
+    if (ctx->nranks <= 1) return ESIMP_OK;
+    return comm_allreduce(ctx, ctx->d_scal + slot0, n, is_max);
+}
+
+// ---------------------------------------------------------------------------- reductions
+__global__ void k_dot(const double* __restrict__ a, const double* __restrict__ b, long long i0, long long i1, double* partial,
+                      unsigned int* ticket, RedOut<1> out) {
+    double acc[1] = {0.0};
+    for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (long long)gridDim.x * blockDim.x)
+        acc[0] = fma(a[i], b[i], acc[0]);
+    grid_reduce<1, false>(acc, partial, ticket, out);
+}
+int vec_dot(esimp_ctx* ctx, const double* a, const double* b, int slot) {
+    RedOut<1> out{{ctx->d_scal + slot}};
+    LAUNCH_STREAM(k_dot, a, b, ctx->own_dof0, ctx->own_dof1, ctx->d_partial, ctx->d_ticket, out);
+    return allreduce_scalars(ctx, slot, 1, false);
+}
+
+// sum_i scale * a[i] * (w ? w[i] : 1) over [i0, i1)
+__global__ void k_sum_scaled(const double* __restrict__ a, const double* __restrict__ w, double scale, long long i0, long long i1,
+                             double* partial, unsigned int* ticket, RedOut<1> out) {
+    double acc[1] = {0.0};
+    for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (long long)gridDim.x * blockDim.x)
+        acc[0] += w ? a[i] * w[i] : a[i];
+    acc[0] *= scale;
+    grid_reduce<1, false>(acc, partial, ticket, out);
+}
+int reduce_sum_scaled(esimp_ctx* ctx, const double* a, const double* w, double scale, int64_t i0, int64_t i1, int slot) {
+    RedOut<1> out{{ctx->d_scal + slot}};
+    LAUNCH_STREAM(k_sum_scaled, a, w, scale, (long long)i0, (long long)i1, ctx->d_partial, ctx->d_ticket, out);
+    return allreduce_scalars(ctx, slot, 1, false);
+}
+
+// change = max|rho_new - rho_old|, gray = #{0.1 < rho_phys < 0.9}  (Optimization.jl:374-378)
+__global__ void k_metrics_cells(const double* __restrict__ rn, const double* __restrict__ ro, const double* __restrict__ ph,
+                                long long i0, long long i1, double* partial, unsigned int* ticket, RedOut<1> outmax,
+                                RedOut<1> outsum, unsigned int* ticket2, double* partial2) {
+    double mx[1] = {0.0}, cnt[1] = {0.0};
+    for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (long long)gridDim.x * blockDim.x) {
+        mx[0] = fmax(mx[0], fabs(rn[i] - ro[i]));
+        double p = ph[i];
+        cnt[0] += (p > 0.1 && p < 0.9) ? 1.0 : 0.0;
+    }
+    grid_reduce<1, true>(mx, partial, ticket, outmax);
+    grid_reduce<1, false>(cnt, partial2, ticket2, outsum);
+}
+__global__ void k_maxabs(const double* __restrict__ a, long long i0, long long i1, double* partial, unsigned int* ticket,
+                         RedOut<1> out) {
+    double mx[1] = {0.0};
+    for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (long long)gridDim.x * blockDim.x)
+        mx[0] = fmax(mx[0], fabs(a[i]));
+    grid_reduce<1, true>(mx, partial, ticket, out);
+}
+int reduce_metrics(esimp_ctx* ctx) {
+    RedOut<1> omax{{ctx->d_scal + SC_CHANGE}}, osum{{ctx->d_scal + SC_GRAY}}, omu{{ctx->d_scal + SC_MAXU}};
+    LAUNCH_STREAM(k_metrics_cells, ctx->d_rho, ctx->d_rho_old, ctx->d_phys, ctx->own_cell0, ctx->own_cell1, ctx->d_partial,
+                  ctx->d_ticket, omax, osum, ctx->d_ticket + 1, ctx->d_partial + RED_BLOCKS);
+    LAUNCH_STREAM(k_maxabs, ctx->d_u, ctx->own_dof0, ctx->own_dof1, ctx->d_partial, ctx->d_ticket, omu);
+    if (ctx->nranks > 1) {
+        // CHANGE and MAXU are max-reduced, GRAY summed; slots are laid out CHANGE, GRAY, MAXU
+        ESIMP_TRY(comm_allreduce(ctx, ctx->d_scal + SC_CHANGE, 1, true));
+        ESIMP_TRY(comm_allreduce(ctx, ctx->d_scal + SC_GRAY, 1, false));
+        ESIMP_TRY(comm_allreduce(ctx, ctx->d_scal + SC_MAXU, 1, true));
+    }
+    return ESIMP_OK;
+}
+
+// ---------------------------------------------------------------------------- Dirichlet fix-up
+// out[d] = m * in[d] on prescribed dofs: the (I-P) m term of apply!
+__global__ void k_fixup(const long long* __restrict__ fixed, long long n, double m, const double* __restrict__ in,
+                        double* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        long long d = fixed[i];
+        out[d] = m * in[d];
+    }
+}
+int vec_fixup_dirichlet(esimp_ctx* ctx, const double* in, double* out) {
+    if (ctx->n_fixed == 0) return ESIMP_OK;
+    int blocks = (int)((ctx->n_fixed + 255) / 256);
+    if (blocks > RED_BLOCKS) blocks = RED_BLOCKS;
+    k_fixup<<<blocks, 256, 0, ctx->stream>>>((const long long*)ctx->d_fixed, ctx->n_fixed, ctx->diag_value, in, out);
+    ctx->launches++;
+    ESIMP_CUDA(cudaGetLastError());
+    return ESIMP_OK;
+}
+
+// ---------------------------------------------------------------------------- PCG kernels
+// r = f - q;  p = Dinv r;  rz = <r, Dinv r>;  rr = <r,r>;  ff = <f,f>
+__global__ void k_pcg_init(const double* __restrict__ f, const double* __restrict__ q, const double* __restrict__ dinv,
+                           double* __restrict__ r, double* __restrict__ p, long long i0, long long i1, double* partial,
+                           unsigned int* ticket, RedOut<3> out) {
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (long long)gridDim.x * blockDim.x) {
+        double fi = f[i], ri = fi - q[i], zi = dinv[i] * ri;
+        r[i] = ri;
+        p[i] = zi;
+        acc[0] = fma(ri, zi, acc[0]);
+        acc[1] = fma(ri, ri, acc[1]);
+        acc[2] = fma(fi, fi, acc[2]);
+    }
+    grid_reduce<3, false>(acc, partial, ticket, out);
+}
+// alpha = rz/pq;  x += alpha p;  r -= alpha q;  rz_new = <r, Dinv r>;  rr = <r,r>
+__global__ void k_pcg_update(const double* __restrict__ p, const double* __restrict__ q, const double* __restrict__ dinv,
+                             double* __restrict__ x, double* __restrict__ r, long long i0, long long i1,
+                             const double* __restrict__ s_rz, const double* __restrict__ s_pq, double* partial,
+                             unsigned int* ticket, RedOut<2> out) {
+    const double alpha = *s_rz / *s_pq;
+    double acc[2] = {0.0, 0.0};
+    for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (long long)gridDim.x * blockDim.x) {
+        x[i] = fma(alpha, p[i], x[i]);
+        double ri = fma(-alpha, q[i], r[i]);
+        r[i] = ri;
+        acc[0] = fma(ri * dinv[i], ri, acc[0]);
+        acc[1] = fma(ri, ri, acc[1]);
+    }
+    grid_reduce<2, false>(acc, partial, ticket, out);
+}
+// beta = rz_new/rz_old;  p = Dinv r + beta p
+__global__ void k_pcg_direction(const double* __restrict__ r, const double* __restrict__ dinv, double* __restrict__ p,
+                                long long i0, long long i1, const double* __restrict__ s_rz_new,
+                                const double* __restrict__ s_rz_old) {
+    const double beta = *s_rz_new / *s_rz_old;
+    for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (long long)gridDim.x * blockDim.x)
+        p[i] = fma(beta, p[i], dinv[i] * r[i]);
+}
+
+int op_apply(esimp_ctx* ctx, double* d_in, double* d_out) {
+    if (ctx->structured) {
+        if (ctx->nranks > 1) ESIMP_TRY(comm_halo_nodes(ctx, d_in));
+        ESIMP_TRY(hex8_matvec(ctx, d_in, d_out, ctx->prm.matvec_variant));
+    } else {
+        ESIMP_TRY(um_matvec(ctx, d_in, d_out));
+    }
+    return vec_fixup_dirichlet(ctx, d_in, d_out);
+}
+
+// Jacobi-PCG on A = P K P + m (I-P), b = P f.  Starts from ctx->d_u (zero or warm start); the
+// prescribed entries of u, r, p stay exactly 0 because f and the initial u are masked.
+int pcg_solve(esimp_ctx* ctx, int* iters, double* relres) {
+    const long long i0 = ctx->own_dof0, i1 = ctx->own_dof1;
+    double* S = ctx->d_scal;
+    // r = f - A u
+    ESIMP_TRY(op_apply(ctx, ctx->d_u, ctx->d_q));
+    {
+        RedOut<3> out{{S + SC_RZ0, S + SC_RR, S + SC_FF}};
+        LAUNCH_STREAM(k_pcg_init, ctx->d_f, ctx->d_q, ctx->d_dinv, ctx->d_r, ctx->d_p, i0, i1, ctx->d_partial, ctx->d_ticket, out);
+        if (ctx->nranks > 1) {
+            ESIMP_TRY(comm_allreduce(ctx, S + SC_RZ0, 1, false));
+            ESIMP_TRY(comm_allreduce(ctx, S + SC_RR, 2, false));  // RR, FF adjacent
+        }
+    }
+    ESIMP_TRY(fetch_scalars(ctx));
+    const double ff = ctx->h_scal[SC_FF];
+    ctx->f_norm2 = ff;
+    const double tol2 = ctx->prm.pcg_rtol * ctx->prm.pcg_rtol * ff;
+    double rr = ctx->h_scal[SC_RR];
+    int it = 0;
+    const int every = ctx->prm.pcg_check_every > 0 ? ctx->prm.pcg_check_every : 1;
+    int status = ESIMP_OK;
+    if (ff == 0.0) {
+        ESIMP_CUDA(cudaMemsetAsync(ctx->d_u, 0, sizeof(double) * ctx->ndof_loc, ctx->stream));
+        rr = 0.0;
+    }
+    while (rr > tol2 && it < ctx->prm.pcg_maxit) {
+        const int cur = it & 1;  // rz slot holding <r,z> of the current residual
+        ESIMP_TRY(op_apply(ctx, ctx->d_p, ctx->d_q));
+        ESIMP_TRY(vec_dot(ctx, ctx->d_p, ctx->d_q, SC_PQ));
+        {
+            RedOut<2> out{{S + SC_RZ0 + (cur ^ 1), S + SC_RR}};
+            LAUNCH_STREAM(k_pcg_update, ctx->d_p, ctx->d_q, ctx->d_dinv, ctx->d_u, ctx->d_r, i0, i1, S + SC_RZ0 + cur, S + SC_PQ,
+                          ctx->d_partial, ctx->d_ticket, out);
+            if (ctx->nranks > 1) {
+                ESIMP_TRY(comm_allreduce(ctx, S + SC_RZ0 + (cur ^ 1), 1, false));
+                ESIMP_TRY(comm_allreduce(ctx, S + SC_RR, 1, false));
+            }
+        }
+        LAUNCH_STREAM(k_pcg_direction, ctx->d_r, ctx->d_dinv, ctx->d_p, i0, i1, S + SC_RZ0 + (cur ^ 1), S + SC_RZ0 + cur);
+        ++it;
+        if (it % every == 0 || it >= ctx->prm.pcg_maxit) {
+            ESIMP_TRY(fetch_scalars(ctx));
+            rr = ctx->h_scal[SC_RR];
+            if (!(rr == rr)) return esimp_fail(ctx, ESIMP_ERR_STATE, "PCG breakdown: residual is NaN");
+        }
+    }
+    if (rr > tol2) status = ESIMP_WARN_PCG_MAXIT;
+    if (iters) *iters = it;
+    if (relres) *relres = ff > 0 ? sqrt(rr / ff) : 0.0;
+    return status;
+}

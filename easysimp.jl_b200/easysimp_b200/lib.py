@@ -1,0 +1,317 @@
+"""ctypes binding of libeasysimp_b200.so (include/easysimp_b200.h).
+
+This is the same binding a Julia host makes with `ccall` (see INTEGRATION.md and
+easysimp.jl_b200/julia/EasySIMPB200.jl); nothing here computes.  There is NO CPU fallback: if
+the shared library is missing or no sm_100 device is present, calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent.parent
+LIB_PATH = Path(os.environ.get("ESIMP_LIB", PKG_DIR / "libeasysimp_b200.so"))
+HEADER_PATH = PKG_DIR.parent / "include" / "easysimp_b200.h"
+
+ESIMP_FILTER_SENSITIVITY, ESIMP_FILTER_DENSITY = 0, 1
+ESIMP_CELL_TET4, ESIMP_CELL_HEX8 = 4, 8
+ESIMP_MATVEC_AUTO, ESIMP_MATVEC_DENSE_ATOMIC, ESIMP_MATVEC_FUSED, ESIMP_MATVEC_FUSED_ATOMIC, ESIMP_MATVEC_FUSED_8x32 = range(5)
+ESIMP_WARN_PCG_MAXIT, ESIMP_WARN_OC_MAXIT = 1, 2
+
+
+class EsimpParams(C.Structure):
+    _fields_ = [
+        ("E0", C.c_double), ("Emin", C.c_double), ("nu", C.c_double), ("p", C.c_double),
+        ("volume_fraction", C.c_double), ("move_limit", C.c_double), ("damping", C.c_double),
+        ("filter_radius", C.c_double), ("filter_type", C.c_int32), ("pcg_maxit", C.c_int32),
+        ("pcg_rtol", C.c_double), ("pcg_check_every", C.c_int32), ("matvec_variant", C.c_int32),
+        ("warm_start", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class EsimpIterStats(C.Structure):
+    _fields_ = [
+        ("energy", C.c_double), ("volume", C.c_double), ("change", C.c_double), ("lam", C.c_double),
+        ("grayness", C.c_double), ("max_u", C.c_double), ("pcg_relres", C.c_double),
+        ("pcg_iters", C.c_int32), ("oc_steps", C.c_int32), ("status", C.c_int32), ("reserved", C.c_int32),
+        ("ms_filter", C.c_double), ("ms_solve", C.c_double), ("ms_sens", C.c_double), ("ms_oc", C.c_double),
+        ("ms_total", C.c_double),
+    ]
+
+
+class EsimpError(RuntimeError):
+    pass
+
+
+_P = C.c_void_p
+_D = C.POINTER(C.c_double)
+_I64 = C.POINTER(C.c_int64)
+_SIGNATURES = {
+    "esimp_version": (C.c_int, []),
+    "esimp_create": (C.c_int, [C.POINTER(_P), C.c_int]),
+    "esimp_destroy": (C.c_int, [_P]),
+    "esimp_last_error": (C.c_char_p, [_P]),
+    "esimp_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "esimp_comm_init": (C.c_int, [_P, C.c_int, C.c_int, C.c_void_p]),
+    "esimp_set_grid_structured": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _I64]),
+    "esimp_set_mesh_unstructured": (C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _D, _I64, _I64]),
+    "esimp_default_params": (C.c_int, [C.POINTER(EsimpParams)]),
+    "esimp_set_params": (C.c_int, [_P, C.POINTER(EsimpParams)]),
+    "esimp_set_dirichlet": (C.c_int, [_P, _I64, C.c_int64]),
+    "esimp_set_load": (C.c_int, [_P, _D]),
+    "esimp_filter_build_structured": (C.c_int, [_P]),
+    "esimp_filter_build_csr": (C.c_int, [_P, _I64, _I64, _D, _D, C.c_double]),
+    "esimp_set_density": (C.c_int, [_P, _D]),
+    "esimp_matvec": (C.c_int, [_P, _D, _D]),
+    "esimp_diagonal": (C.c_int, [_P, _D]),
+    "esimp_solve": (C.c_int, [_P, _D, C.POINTER(C.c_int), _D]),
+    "esimp_sensitivities": (C.c_int, [_P, _D, _D]),
+    "esimp_filter_sens": (C.c_int, [_P, _D, _D, _D]),
+    "esimp_filter_dens": (C.c_int, [_P, _D, _D]),
+    "esimp_filter_dens_T": (C.c_int, [_P, _D, _D]),
+    "esimp_oc": (C.c_int, [_P, _D, _D, _D, _D, _D, C.POINTER(C.c_int)]),
+    "esimp_init_design": (C.c_int, [_P, _D]),
+    "esimp_iterate": (C.c_int, [_P, C.POINTER(EsimpIterStats)]),
+    "esimp_final_analysis": (C.c_int, [_P, _D, _D, C.POINTER(C.c_int)]),
+    "esimp_get_design": (C.c_int, [_P, _D]),
+    "esimp_get_physical_density": (C.c_int, [_P, _D]),
+    "esimp_get_displacement": (C.c_int, [_P, _D]),
+    "esimp_set_displacement": (C.c_int, [_P, _D]),
+    "esimp_n_dofs": (C.c_int64, [_P]),
+    "esimp_n_cells": (C.c_int64, [_P]),
+    "esimp_bench_matvec": (C.c_int, [_P, C.c_int, _D, _D]),
+    "esimp_launch_count": (C.c_int64, [_P]),
+}
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the shared library and declare every prototype.  Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise EsimpError(f"{LIB_PATH} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(there is no CPU fallback)")
+        lib = C.CDLL(str(LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def exported_symbols():
+    return list(_SIGNATURES)
+
+
+def _f64(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_D)
+
+
+def _i64(a):
+    a = np.ascontiguousarray(a, dtype=np.int64)
+    return a, a.ctypes.data_as(_I64)
+
+
+class Context:
+    """Thin RAII wrapper around esimp_ctx*; every method is one C-ABI call with host buffers."""
+
+    def __init__(self, device: int = -1):
+        self.lib = load_library()
+        self._h = _P()
+        st = self.lib.esimp_create(C.byref(self._h), device)
+        if st < 0:
+            raise EsimpError(f"esimp_create failed ({st}): {self.lib.esimp_last_error(None).decode()}")
+        self.params = EsimpParams()
+        self.lib.esimp_default_params(C.byref(self.params))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.esimp_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _chk(self, st, what):
+        if st < 0:
+            raise EsimpError(f"{what} failed ({st}): {self.lib.esimp_last_error(self._h).decode()}")
+        return st
+
+    # -- setup
+    def comm_init(self, rank, nranks, uid: bytes):
+        buf = C.create_string_buffer(uid, 128)
+        self._chk(self.lib.esimp_comm_init(self._h, rank, nranks, buf), "esimp_comm_init")
+
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(self.params, k):
+                raise AttributeError(k)
+            setattr(self.params, k, v)
+        self._chk(self.lib.esimp_set_params(self._h, C.byref(self.params)), "esimp_set_params")
+
+    def set_grid_structured(self, nx, ny, nz, hx, hy, hz, dof_of_node=None):
+        ptr = None
+        if dof_of_node is not None:
+            keep, ptr = _i64(np.asarray(dof_of_node).reshape(-1))
+        self._chk(self.lib.esimp_set_grid_structured(self._h, nx, ny, nz, hx, hy, hz, ptr), "esimp_set_grid_structured")
+
+    def set_mesh_unstructured(self, celltype, xyz, conn, celldofs):
+        k1, p1 = _f64(np.asarray(xyz).reshape(-1))
+        k2, p2 = _i64(np.asarray(conn).reshape(-1))
+        k3, p3 = _i64(np.asarray(celldofs).reshape(-1))
+        n_cells = k2.size // celltype
+        self._chk(self.lib.esimp_set_mesh_unstructured(self._h, celltype, n_cells, k1.size // 3, p1, p2, p3),
+                  "esimp_set_mesh_unstructured")
+
+    def set_dirichlet(self, dofs):
+        k, p = _i64(np.asarray(dofs).reshape(-1))
+        self._chk(self.lib.esimp_set_dirichlet(self._h, p, k.size), "esimp_set_dirichlet")
+
+    def set_load(self, f):
+        k, p = _f64(f)
+        assert k.size == self.n_dofs
+        self._chk(self.lib.esimp_set_load(self._h, p), "esimp_set_load")
+
+    def filter_build_structured(self):
+        self._chk(self.lib.esimp_filter_build_structured(self._h), "esimp_filter_build_structured")
+
+    def filter_build_csr(self, rowptr, col, centers, volumes, R):
+        k1, p1 = _i64(rowptr)
+        k2, p2 = _i64(col)
+        k3, p3 = _f64(np.asarray(centers).reshape(-1))
+        k4, p4 = _f64(volumes)
+        self._chk(self.lib.esimp_filter_build_csr(self._h, p1, p2, p3, p4, float(R)), "esimp_filter_build_csr")
+
+    @property
+    def n_dofs(self):
+        return int(self.lib.esimp_n_dofs(self._h))
+
+    @property
+    def n_cells(self):
+        return int(self.lib.esimp_n_cells(self._h))
+
+    @property
+    def launch_count(self):
+        return int(self.lib.esimp_launch_count(self._h))
+
+    # -- stage calls
+    def set_density(self, rho):
+        k, p = _f64(rho)
+        assert k.size == self.n_cells
+        self._chk(self.lib.esimp_set_density(self._h, p), "esimp_set_density")
+
+    def matvec(self, u):
+        k, p = _f64(u)
+        assert k.size == self.n_dofs
+        y = np.empty(self.n_dofs)
+        self._chk(self.lib.esimp_matvec(self._h, p, y.ctypes.data_as(_D)), "esimp_matvec")
+        return y
+
+    def diagonal(self):
+        d = np.empty(self.n_dofs)
+        self._chk(self.lib.esimp_diagonal(self._h, d.ctypes.data_as(_D)), "esimp_diagonal")
+        return d
+
+    def solve(self, want_u=True):
+        u = np.empty(self.n_dofs) if want_u else None
+        it = C.c_int(0)
+        rr = C.c_double(0)
+        st = self._chk(self.lib.esimp_solve(self._h, u.ctypes.data_as(_D) if want_u else None, C.byref(it), C.byref(rr)),
+                       "esimp_solve")
+        return u, it.value, rr.value, st
+
+    def sensitivities(self, want_dc=True):
+        dc = np.empty(self.n_cells) if want_dc else None
+        en = C.c_double(0)
+        self._chk(self.lib.esimp_sensitivities(self._h, dc.ctypes.data_as(_D) if want_dc else None, C.byref(en)),
+                  "esimp_sensitivities")
+        return dc, en.value
+
+    def filter_sens(self, rho, dc):
+        k1, p1 = _f64(rho)
+        k2, p2 = _f64(dc)
+        out = np.empty(self.n_cells)
+        self._chk(self.lib.esimp_filter_sens(self._h, p1, p2, out.ctypes.data_as(_D)), "esimp_filter_sens")
+        return out
+
+    def filter_dens(self, rho):
+        k1, p1 = _f64(rho)
+        out = np.empty(self.n_cells)
+        self._chk(self.lib.esimp_filter_dens(self._h, p1, out.ctypes.data_as(_D)), "esimp_filter_dens")
+        return out
+
+    def filter_dens_T(self, s):
+        k1, p1 = _f64(s)
+        out = np.empty(self.n_cells)
+        self._chk(self.lib.esimp_filter_dens_T(self._h, p1, out.ctypes.data_as(_D)), "esimp_filter_dens_T")
+        return out
+
+    def oc(self, rho, dc, dv):
+        k1, p1 = _f64(rho)
+        k2, p2 = _f64(dc)
+        k3, p3 = _f64(dv)
+        out = np.empty(self.n_cells)
+        lam = C.c_double(0)
+        steps = C.c_int(0)
+        st = self._chk(self.lib.esimp_oc(self._h, p1, p2, p3, out.ctypes.data_as(_D), C.byref(lam), C.byref(steps)), "esimp_oc")
+        return out, lam.value, steps.value, st
+
+    # -- loop
+    def init_design(self, rho=None):
+        ptr = None
+        if rho is not None:
+            k, ptr = _f64(rho)
+        self._chk(self.lib.esimp_init_design(self._h, ptr), "esimp_init_design")
+
+    def iterate(self) -> EsimpIterStats:
+        s = EsimpIterStats()
+        self._chk(self.lib.esimp_iterate(self._h, C.byref(s)), "esimp_iterate")
+        return s
+
+    def final_analysis(self):
+        e = C.c_double(0)
+        v = C.c_double(0)
+        it = C.c_int(0)
+        self._chk(self.lib.esimp_final_analysis(self._h, C.byref(e), C.byref(v), C.byref(it)), "esimp_final_analysis")
+        return e.value, v.value, it.value
+
+    def get_design(self):
+        out = np.empty(self.n_cells)
+        self._chk(self.lib.esimp_get_design(self._h, out.ctypes.data_as(_D)), "esimp_get_design")
+        return out
+
+    def get_physical_density(self):
+        out = np.empty(self.n_cells)
+        self._chk(self.lib.esimp_get_physical_density(self._h, out.ctypes.data_as(_D)), "esimp_get_physical_density")
+        return out
+
+    def get_displacement(self):
+        out = np.empty(self.n_dofs)
+        self._chk(self.lib.esimp_get_displacement(self._h, out.ctypes.data_as(_D)), "esimp_get_displacement")
+        return out
+
+    def set_displacement(self, u):
+        k, p = _f64(u)
+        assert k.size == self.n_dofs
+        self._chk(self.lib.esimp_set_displacement(self._h, p), "esimp_set_displacement")
+
+    def bench_matvec(self, reps):
+        ms = C.c_double(0)
+        by = C.c_double(0)
+        self._chk(self.lib.esimp_bench_matvec(self._h, reps, C.byref(ms), C.byref(by)), "esimp_bench_matvec")
+        return ms.value, by.value
+
+
+def comm_unique_id() -> bytes:
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    st = lib.esimp_comm_unique_id(buf)
+    if st < 0:
+        raise EsimpError(f"esimp_comm_unique_id failed: {lib.esimp_last_error(None).decode()}")
+    return buf.raw

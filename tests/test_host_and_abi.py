@@ -1,0 +1,121 @@
+"""CPU tests of the host logic and of the C-ABI boundary: the shared library loads and exports every
+symbol include/easysimp_b200.h declares; without a GPU the product path fails loudly (no fallback);
+the host mirror reproduces the oracle's grid / dof / node-selection / filter-cache conventions."""
+import ctypes
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import easysimp_b200 as es
+from easysimp_b200 import lib as eslib
+from oracle import simp_oracle as o
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def header_functions():
+    text = (ROOT / "include" / "easysimp_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(esimp_[a-z_A-Z0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = es.load_library()
+    declared = header_functions()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert sorted(eslib.exported_symbols()) == declared, "ctypes prototypes and header are out of sync"
+    assert lib.esimp_version() == 100
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(eslib.EsimpParams) == 8 * 8 + 4 * 2 + 8 + 4 * 4
+    assert ctypes.sizeof(eslib.EsimpIterStats) == 7 * 8 + 4 * 4 + 5 * 8
+    p = eslib.EsimpParams()
+    es.load_library().esimp_default_params(ctypes.byref(p))
+    # OptimizationParameters defaults, Optimization.jl:87-102
+    assert (p.E0, p.Emin, p.nu, p.p, p.volume_fraction, p.move_limit, p.damping, p.filter_radius) == (1.0, 1e-9, 0.3, 3.0, 0.5, 0.2, 0.5, 1.5)
+    assert p.filter_type == eslib.ESIMP_FILTER_SENSITIVITY
+
+
+def test_no_cpu_fallback_without_device():
+    """Without a usable sm_100 device esimp_create must fail with a message; nothing computes on CPU."""
+    try:
+        import torch
+
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    with pytest.raises(es.EsimpError, match="no CUDA device|CPU fallback|sm_"):
+        es.Context(0)
+
+
+def test_product_does_not_import_oracle():
+    """The product path must never route through oracle/ (it is test infrastructure)."""
+    pkg = ROOT / "easysimp.jl_b200"
+    for f in list(pkg.rglob("*.py")) + list(pkg.rglob("*.cu")) + list(pkg.rglob("*.cuh")) + list(pkg.rglob("*.jl")):
+        text = f.read_text()
+        assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+        assert "simp_oracle" not in text and "oracle/" not in text, f
+
+
+@pytest.mark.parametrize("nel,left,right", [((5, 3, 2), (0, 0, 0), (5, 3, 2)), ((4, 4, 3), (-1.0, 0.5, 0.0), (1.0, 1.5, 0.6))])
+def test_host_grid_and_dofs_match_oracle(nel, left, right):
+    g = es.generate_grid(es.Hexahedron, nel, left, right)
+    go = o.generate_grid_hex(nel, left, right)
+    assert np.allclose(g.coords, go.coords, atol=0, rtol=0) and np.array_equal(g.cells, go.cells)
+    from easysimp_b200.host import _distribute_dofs
+
+    assert np.array_equal(_distribute_dofs(g), o.distribute_dofs(go))
+    assert abs(es.estimate_element_size(g) - o.estimate_element_size(go)) <= 1e-15
+    assert np.allclose(es.calculate_element_volumes(g), o.element_volumes(go), rtol=1e-14)
+    assert np.array_equal(es.calculate_cell_centers(g), o.cell_centers(go))
+
+
+def test_host_node_selection_matches_reference_recipe():
+    g = es.generate_grid(es.Hexahedron, (60, 20, 4), (0, 0, 0), (60.0, 20.0, 4.0))
+    fixed = es.select_nodes_by_plane(g, [0.0, 0.0, 0.0], [1.0, 0.0, 0.0], 1e-3)
+    force = es.select_nodes_by_circle(g, [60.0, 0.0, 2.0], [1.0, 0.0, 0.0], 1.0)
+    assert len(fixed) == 21 * 5 and len(force) == 4  # README.md:122-124
+    go = o.generate_grid_hex((60, 20, 4))
+    assert fixed == o.select_nodes_by_plane(go, [0, 0, 0], [1, 0, 0], 1e-3)
+    assert force == o.select_nodes_by_circle(go, [60.0, 0.0, 2.0], [1, 0, 0], 1.0)
+
+
+def test_host_unstructured_filter_cache_matches_oracle():
+    go = o.generate_grid_hex((6, 4, 3))
+    rng = np.random.default_rng(0)
+    coords = go.coords + 0.05 * rng.standard_normal(go.coords.shape)
+    g = es.Grid(coords, go.cells.copy(), None)
+    V = es.calculate_element_volumes(g)
+    gu = o.Grid(coords, go.cells.copy(), None)
+    assert np.allclose(V, o.element_volumes(gu), rtol=1e-13)
+    fc = es.create_filter_cache(g, 1.5, V)
+    fo = o.create_filter_cache(gu, 1.5, V)
+    assert fc.filter_radius == fo.radius and np.array_equal(fc.rowptr, fo.rowptr) and np.array_equal(fc.col, fo.col)
+
+
+def test_optimization_parameters_defaults_match_reference():
+    p = es.OptimizationParameters()
+    assert (p.E0, p.Emin, p.nu, p.p, p.volume_fraction, p.max_iterations, p.tolerance, p.filter_radius, p.filter_type,
+            p.move_limit, p.damping, p.use_cache, p.export_interval, p.export_path, p.task_name, p.tolerance_checkpoints) == (
+        1.0, 1e-9, 0.3, 3.0, 0.5, 200, 0.01, 1.5, "sensitivity", 0.2, 0.5, True, 0, "", "SIMP_Optimization", [])
+
+
+def test_slab_partition_covers_grid():
+    for nx, R, he in [(512, 8, 1), (60, 4, 2), (7, 3, 1), (5, 1, 1)]:
+        slabs = [es.slab_partition(nx, r, R, he) for r in range(R)]
+        assert slabs[0].ex0 == 0 and slabs[-1].ex1 == nx
+        owned_planes = []
+        for s in slabs:
+            assert s.ex1 > s.ex0
+            owned_planes += list(range(s.gp0 + s.own_p0, s.gp0 + s.own_p1))
+            # layers the operator visits touch exactly the stored planes
+            assert s.ge0 + s.mv_e0 == s.gp0 and s.ge0 + s.mv_e1 == s.gp0 + s.npx - 1
+            assert s.nex == (s.ex1 - s.ex0) + s.halo_e * ((s.rank > 0) + (s.rank < R - 1))
+        assert owned_planes == list(range(nx + 1))
