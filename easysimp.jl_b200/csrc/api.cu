@@ -1,6 +1,7 @@
 // api.cu -- the C ABI (include/easysimp_b200.h): context lifecycle, host<->device marshalling, the
 // stage calls used by the parity tests and the fused SIMP iteration (Optimization.jl:271-379).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -8,6 +9,7 @@
 #include "ctx.cuh"
 
 int op_apply(esimp_ctx* ctx, double* d_in, double* d_out);  // vector_ops.cu
+int op_apply_general(esimp_ctx* ctx, double* d_in, double* d_tmp, double* d_out);
 
 static std::string g_create_error;
 
@@ -106,6 +108,7 @@ int esimp_create(esimp_ctx** out, int device) {
     esimp_ctx* ctx = new esimp_ctx();
     ctx->device = device;
     esimp_default_params(&ctx->prm);
+    if (const char* e = getenv("ESIMP_FUSED_CHUNK")) ctx->fused_chunk = atoi(e);
     auto bail = [&](const char* what) {
         std::string msg = std::string(what) + ": " + cudaGetErrorString(cudaGetLastError());
         delete ctx;
@@ -370,7 +373,7 @@ int esimp_matvec(esimp_ctx* ctx, const double* u, double* y) {
     NEED(ctx->density_set, "esimp_set_density first");
     if (!u || !y) return esimp_fail(ctx, ESIMP_ERR_ARG, "NULL vector");
     ESIMP_TRY(upload_dofs(ctx, u, ctx->d_p));
-    ESIMP_TRY(op_apply(ctx, ctx->d_p, ctx->d_q));
+    ESIMP_TRY(op_apply_general(ctx, ctx->d_p, ctx->d_r, ctx->d_q));
     return download_dofs(ctx, ctx->d_q, y);
 }
 
@@ -629,6 +632,13 @@ int esimp_bench_matvec(esimp_ctx* ctx, int reps, double* ms_avg, double* bytes_p
     NEED(ctx->density_set, "esimp_set_density first");
     if (reps < 1) return esimp_fail(ctx, ESIMP_ERR_ARG, "reps < 1");
     ESIMP_CUDA(cudaMemcpyAsync(ctx->d_p, ctx->d_f, sizeof(double) * ctx->ndof_loc, cudaMemcpyDeviceToDevice, ctx->stream));
+    {
+        const double m = ctx->diag_value;
+        ctx->diag_value = 0.0;
+        int s = vec_fixup_dirichlet(ctx, ctx->d_p, ctx->d_p);  // operator input must vanish on prescribed dofs
+        ctx->diag_value = m;
+        ESIMP_TRY(s);
+    }
     ESIMP_TRY(op_apply(ctx, ctx->d_p, ctx->d_q));  // warm-up
     cudaEventRecord(ctx->ev[0], ctx->stream);
     for (int i = 0; i < reps; ++i) ESIMP_TRY(op_apply(ctx, ctx->d_p, ctx->d_q));

@@ -90,6 +90,7 @@ struct esimp_ctx {
     int own_e0 = 0, own_e1 = 0;  // owned local element layers
     int mv_e0 = 0, mv_e1 = 0;    // element layers the operator visits (owned + redundant left layer)
     int halo_e = 0;              // ghost element layers per interior side
+    int fused_chunk = 0;         // >0: force the x-chunk length of the fused operator (tuning)
     bool has_left = false, has_right = false;
     int64_t n_dofs_global = 0, n_cells_global = 0;
     int64_t ndof_loc = 0, ncell_loc = 0;  // stored (incl. ghosts)

@@ -19,6 +19,8 @@
 #include <math.h>
 #include <string.h>
 
+#include <type_traits>
+
 #include "ctx.cuh"
 
 // ---------------------------------------------------------------------------- constants
@@ -247,7 +249,7 @@ __global__ void __launch_bounds__(128) k_matvec_dense_atomic(GridDev g, int le0,
 }
 
 // ---------------------------------------------------------------------------- V2: fused x-march
-// Block = TZ lanes (z, fastest axis) x TY warps-rows (y).  Thread (ty,tz) owns the cell column
+// Block = TZ lanes (z, fastest axis) x TY rows (y).  Thread (ty,tz) owns the cell column
 // (Y0+ty, Z0+tz) and marches along x through [Lstart, Lend).  Per step it
 //   1. reads the 4 nodes of the new plane from the shared input tile (3 comps) -> Fn (12 values)
 //   2. v = E (Fn +- Fp)  (E folded into the x butterfly), w = K~ v  (45 FMAs, constant operands)
@@ -255,40 +257,51 @@ __global__ void __launch_bounds__(128) k_matvec_dense_atomic(GridDev g, int le0,
 //   4. inverse 2-D butterfly -> 4 corner contributions; corner (0,0) stays in registers, the other
 //      three go through shared memory to the threads that own those nodes
 //   5. one __syncthreads per plane; node totals are stored (owner tiles) or red.add'ed (atomic tiles)
+// The INPUT MUST BE ZERO ON PRESCRIBED DOFS (op_apply guarantees it): no mask is read here, so the
+// plane prefetched two steps ahead sits in registers untouched until it is staged (ncu r1: the
+// in-kernel mask select made every prefetch a long-scoreboard stall).
+// Shared output tiles carry a zero border (row 0 / column 0) so that the gather needs no guards.
 // ATOMIC=false: tiles overlap by one cell row/column, a tile owns the nodes interior to it and the
 //   perimeter cells are computed twice: deterministic, no zero-fill, ~(1-1/TY)(1-1/TZ) efficient.
 // ATOMIC=true : tiles do not overlap; perimeter nodes are combined with atomicAdd into a y whose
-//   perimeter rows/columns were zeroed first.
+//   perimeter rows/columns were zeroed first (ncu r1: 2x slower than owner tiles on B200).
 template <int TY, int TZ>
 struct FusedSmem {
-    double in[2][3][TY + 1][TZ + 1];  // masked u of a node plane, double buffered
-    double out[2][3][3][TY][TZ];      // corner contributions c01, c10, c11, double buffered
+    double in[4][3][TY + 1][TZ + 1];      // u of a node plane: 4-deep cp.async ring
+    double E[4][TY][TZ];                  // modulus of the cell layer consumed together with that plane
+    double out[2][3][3][TY + 1][TZ + 1];  // corner contributions c01, c10, c11 at [ty+1][tz+1]; borders stay 0
 };
 
-template <int TY, int TZ, bool ATOMIC>
-__global__ void __launch_bounds__(TY* TZ) k_matvec_fused(GridDev g, int le0, int le1, int ps0, int ps1, int chunk,
-                                                         const double* __restrict__ E, const uint8_t* __restrict__ mask,
-                                                         const double* __restrict__ u, double* __restrict__ y) {
+// 8-byte asynchronous global->shared copy (LDGSTS); !valid zero-fills the destination
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool valid) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+template <int TY, int TZ, bool ATOMIC, int MINB>
+__global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le0, int le1, int ps0, int ps1, int chunk,
+                                                               const double* __restrict__ E, const double* __restrict__ u,
+                                                               double* __restrict__ y) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FusedSmem<TY, TZ>& sm = *reinterpret_cast<FusedSmem<TY, TZ>*>(smem_raw);
-    const int tz = threadIdx.x % TZ, ty = threadIdx.x / TZ;
     const int tid = threadIdx.x;
+    const int tz = tid % TZ, ty = tid / TZ;
     constexpr int SY = ATOMIC ? TY : TY - 1, SZ = ATOMIC ? TZ : TZ - 1;
     const int Y0 = blockIdx.y * SY - (ATOMIC ? 0 : 1), Z0 = blockIdx.x * SZ - (ATOMIC ? 0 : 1);
     const int ey = Y0 + ty, ez = Z0 + tz;  // my cell column == my node (low corner)
     const bool cell_ok = ey >= 0 && ey < g.ny && ez >= 0 && ez < g.nz;
     const bool node_ok = ey >= 0 && ey <= g.ny && ez >= 0 && ez <= g.nz;
-    // halo node of the input tile handled by this thread (row TY, column TZ)
-    int hj = -1, hk = -1;
-    if (tid <= TZ) {
-        hj = TY;
-        hk = tid;
-    } else if (tid < TZ + 1 + TY) {
-        hj = tid - TZ - 1;
-        hk = TZ;
-    }
+    // halo node of the input tile handled by this thread (row TY: tid 0..TZ, column TZ: the next TY)
+    const bool has_halo = tid < TZ + 1 + TY;
+    const int hj = tid <= TZ ? TY : tid - TZ - 1, hk = tid <= TZ ? tid : TZ;
     const int hy = Y0 + hj, hz = Z0 + hk;
-    const bool halo_ok = hj >= 0 && hy >= 0 && hy <= g.ny && hz >= 0 && hz <= g.nz;
+    const bool halo_ok = has_halo && hy >= 0 && hy <= g.ny && hz >= 0 && hz <= g.nz;
 
     // node planes this block owns and the cell layers that touch them
     const int P0 = ps0 + blockIdx.z * chunk, P1 = min(P0 + chunk, ps1);
@@ -296,87 +309,77 @@ __global__ void __launch_bounds__(TY* TZ) k_matvec_fused(GridDev g, int le0, int
     if (Lstart >= Lend) return;
     const int nsteps = Lend - Lstart;
     const int pl0 = Lstart + g.e2p;  // first node plane read
+    const long long plane = g.plane, plane3 = 3 * g.plane;
 
-    const long long noff = (long long)ey * (g.nz + 1) + ez;       // node offset within a plane
-    const long long hoff = (long long)hy * (g.nz + 1) + hz;
-    const long long coff = (long long)ey * g.nz + ez;              // cell offset within a layer
+    // running pointers (strength-reduced addressing: one add per plane)
+    const double* pu = u + (long long)pl0 * plane3 + (node_ok ? (long long)ey * (g.nz + 1) + ez : 0);
+    const double* ph = u + (long long)pl0 * plane3 + (halo_ok ? (long long)hy * (g.nz + 1) + hz : 0);
+    const double* pE = E + (long long)Lstart * g.eplane + (cell_ok ? (long long)ey * g.nz + ez : 0);
+    double* py = y + (long long)pl0 * plane3 + (node_ok ? (long long)ey * (g.nz + 1) + ez : 0);
+    double* pyh = y + (long long)pl0 * plane3 + (halo_ok ? (long long)hy * (g.nz + 1) + hz : 0);
+    const bool own_store = node_ok && ty >= 1 && tz >= 1;
 
-    double un[3], uh[3];
-    auto load_plane = [&](int lp) {
-        if (node_ok) {
-            uint8_t m = mask[(long long)lp * g.plane + noff];
+    // zero the output tiles once (their borders are never written again)
+    for (int i = tid; i < 2 * 9 * (TY + 1) * (TZ + 1); i += TY * TZ) (&sm.out[0][0][0][0][0])[i] = 0.0;
+
+    // issue the asynchronous copies of plane pl0+k (and of the modulus of layer Lstart+k-1, which is
+    // consumed in the same step) into ring slot k&3; always commits one group so that wait_group counts
+    auto issue_plane = [&](int k) {
+        if (k <= nsteps) {
+            const int buf = k & 3;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                double v = u[(long long)(lp * 3 + c) * g.plane + noff];
-                un[c] = ((m >> c) & 1) ? 0.0 : v;
+            for (int c = 0; c < 3; ++c) cp_async8(&sm.in[buf][c][ty][tz], pu + c * plane, node_ok);
+            if (has_halo) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) cp_async8(&sm.in[buf][c][hj][hk], ph + c * plane, halo_ok);
             }
-        } else {
-            un[0] = un[1] = un[2] = 0.0;
-        }
-        if (hj >= 0) {
-            if (halo_ok) {
-                uint8_t m = mask[(long long)lp * g.plane + hoff];
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    double v = u[(long long)(lp * 3 + c) * g.plane + hoff];
-                    uh[c] = ((m >> c) & 1) ? 0.0 : v;
-                }
-            } else {
-                uh[0] = uh[1] = uh[2] = 0.0;
+            if (k >= 1) {
+                cp_async8(&sm.E[buf][ty][tz], pE, cell_ok);
+                pE += g.eplane;
             }
+            pu += plane3;
+            ph += plane3;
         }
-    };
-    auto stage_plane = [&](int buf) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c) sm.in[buf][c][ty][tz] = un[c];
-        if (hj >= 0) {
-#pragma unroll
-            for (int c = 0; c < 3; ++c) sm.in[buf][c][hj][hk] = uh[c];
-        }
+        cp_async_commit();
     };
     auto face_modes = [&](int buf, double (&F)[3][4]) {
 #pragma unroll
         for (int c = 0; c < 3; ++c)
             fwd2d(sm.in[buf][c][ty][tz], sm.in[buf][c][ty + 1][tz], sm.in[buf][c][ty][tz + 1], sm.in[buf][c][ty + 1][tz + 1], F[c]);
     };
-    // combine the corner contributions of plane `lp` and write the node totals
-    auto flush_plane = [&](int buf, int lp, const double (&c00)[3]) {
-        const bool store = lp >= P0 && lp < P1;
-        if (!store) return;
+    auto put_corners = [&](int buf, int c, double y01, double y10, double y11) {
+        sm.out[buf][0][c][ty + 1][tz + 1] = y01;  // -> node (ty, tz+1)
+        sm.out[buf][1][c][ty + 1][tz + 1] = y10;  // -> node (ty+1, tz)
+        sm.out[buf][2][c][ty + 1][tz + 1] = y11;  // -> node (ty+1, tz+1)
+    };
+    // combine the corner contributions of the plane py points at, write the node totals, advance py
+    auto flush_plane = [&](int buf, bool store, const double (&c00)[3]) {
+        if (store) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            double s = c00[c];
-            if (tz >= 1) s += sm.out[buf][0][c][ty][tz - 1];
-            if (ty >= 1) s += sm.out[buf][1][c][ty - 1][tz];
-            if (ty >= 1 && tz >= 1) s += sm.out[buf][2][c][ty - 1][tz - 1];
-            if (node_ok) {
-                double* dst = &y[(long long)(lp * 3 + c) * g.plane + noff];
-                if (ty >= 1 && tz >= 1) {
-                    *dst = s;
-                } else if (ATOMIC) {
-                    atomicAdd(dst, s);
+            for (int c = 0; c < 3; ++c) {
+                double s = c00[c] + sm.out[buf][0][c][ty + 1][tz] + sm.out[buf][1][c][ty][tz + 1] + sm.out[buf][2][c][ty][tz];
+                if (own_store) {
+                    py[c * plane] = s;
+                } else if (ATOMIC && node_ok) {
+                    atomicAdd(&py[c * plane], s);
                 }
-            }
-            if (ATOMIC && hj >= 0 && halo_ok) {
-                double h = 0.0;
-                if (hj == TY) {  // top row: cells (TY-1, hk) and (TY-1, hk-1)
-                    if (hk < TZ) h += sm.out[buf][1][c][TY - 1][hk];
-                    if (hk >= 1) h += sm.out[buf][2][c][TY - 1][hk - 1];
-                } else {  // right column: cells (hj, TZ-1) and (hj-1, TZ-1)
-                    h += sm.out[buf][0][c][hj][TZ - 1];
-                    if (hj >= 1) h += sm.out[buf][2][c][hj - 1][TZ - 1];
+                if (ATOMIC && halo_ok) {
+                    // top row (hj == TY): cells (TY-1, hk) and (TY-1, hk-1); right column: (hj, TZ-1), (hj-1, TZ-1)
+                    double h = (hj == TY) ? ((hk < TZ ? sm.out[buf][1][c][TY][hk + 1] : 0.0) + sm.out[buf][2][c][TY][hk])
+                                          : (sm.out[buf][0][c][hj + 1][TZ] + sm.out[buf][2][c][hj][TZ]);
+                    atomicAdd(&pyh[c * plane], h);
                 }
-                atomicAdd(&y[(long long)(lp * 3 + c) * g.plane + hoff], h);
             }
         }
+        py += plane3;
+        pyh += plane3;
     };
 
-    // ---- prologue: planes pl0 and pl0+1 into the two input buffers
-    load_plane(pl0);
-    stage_plane(0);
-    load_plane(pl0 + 1);
-    stage_plane(1);
-    double Enext = cell_ok ? E[(long long)Lstart * g.eplane + coff] : 0.0;
+    // ---- prologue: planes pl0 .. pl0+3 in flight, the first two landed
+    issue_plane(0);
+    issue_plane(1);
+    issue_plane(2);
+    cp_async_wait<1>();
     __syncthreads();
     double Fp[3][4], Gpp[3][4];
     face_modes(0, Fp);
@@ -384,15 +387,17 @@ __global__ void __launch_bounds__(TY* TZ) k_matvec_fused(GridDev g, int le0, int
     for (int c = 0; c < 3; ++c)
 #pragma unroll
         for (int b = 0; b < 4; ++b) Gpp[c][b] = 0.0;
-    if (nsteps > 1) load_plane(pl0 + 2);
-    __syncthreads();  // in[0] is re-staged in step 0: every thread must have read it
+    issue_plane(3);
 
-#pragma unroll 1
-    for (int it = 0; it < nsteps; ++it) {
-        const double Ee = Enext;
-        if (it + 1 < nsteps && cell_ok) Enext = E[(long long)(Lstart + it + 1) * g.eplane + coff];
+    int lp = pl0;  // plane the current step completes
+    // one marching step; BUF = it & 1 is a compile-time constant (loop unrolled by two below) so that
+    // every shared-memory access is [thread base + immediate]
+    auto step = [&](auto bufc, int it) {
+        constexpr int BUF = decltype(bufc)::value;
+        const int ring = (it + 1) & 3;  // slot of plane pl0+it+1 and of this layer's modulus
+        const double Ee = sm.E[ring][ty][tz];
         double Fn[3][4];
-        face_modes((it + 1) & 1, Fn);
+        face_modes(ring, Fn);
         // x butterfly with the modulus folded in: v0 = E (Fn + Fp), v1 = E (Fn - Fp)
         double v[3][8], w[3][8];
 #pragma unroll
@@ -416,15 +421,21 @@ __global__ void __launch_bounds__(TY* TZ) k_matvec_fused(GridDev g, int le0, int
             }
             double y10, y01, y11;
             inv2d(A, c00[c], y10, y01, y11);
-            sm.out[it & 1][0][c][ty][tz] = y01;  // -> node (ty, tz+1)
-            sm.out[it & 1][1][c][ty][tz] = y10;  // -> node (ty+1, tz)
-            sm.out[it & 1][2][c][ty][tz] = y11;  // -> node (ty+1, tz+1)
+            put_corners(BUF, c, y01, y10, y11);
         }
-        if (it + 1 < nsteps) stage_plane(it & 1);  // plane pl0+it+2, prefetched last step
+        cp_async_wait<1>();  // plane pl0+it+2 has landed (only the newest group may be pending)
         __syncthreads();
-        flush_plane(it & 1, pl0 + it, c00);
-        if (it + 2 < nsteps) load_plane(pl0 + it + 3);
+        flush_plane(BUF, lp >= P0 && lp < P1, c00);
+        issue_plane(it + 4);  // into the slot of plane pl0+it, which nobody reads any more
+        ++lp;
+    };
+    int it = 0;
+#pragma unroll 1
+    for (; it + 1 < nsteps; it += 2) {
+        step(std::integral_constant<int, 0>{}, it);
+        step(std::integral_constant<int, 1>{}, it + 1);
     }
+    if (it < nsteps) step(std::integral_constant<int, 0>{}, it);
     // ---- epilogue: the last plane only receives Gp of the last cell
     {
         double c00[3];
@@ -432,12 +443,10 @@ __global__ void __launch_bounds__(TY* TZ) k_matvec_fused(GridDev g, int le0, int
         for (int c = 0; c < 3; ++c) {
             double y10, y01, y11;
             inv2d(Gpp[c], c00[c], y10, y01, y11);
-            sm.out[nsteps & 1][0][c][ty][tz] = y01;
-            sm.out[nsteps & 1][1][c][ty][tz] = y10;
-            sm.out[nsteps & 1][2][c][ty][tz] = y11;
+            put_corners(nsteps & 1, c, y01, y10, y11);
         }
         __syncthreads();
-        flush_plane(nsteps & 1, pl0 + nsteps, c00);
+        flush_plane(nsteps & 1, lp >= P0 && lp < P1, c00);
     }
 }
 
@@ -452,21 +461,22 @@ __global__ void k_zero_perimeter(GridDev g, int ps0, int ps1, double* __restrict
     }
 }
 
-template <int TY, int TZ, bool ATOMIC>
+template <int TY, int TZ, bool ATOMIC, int MINB>
 static int launch_fused(esimp_ctx* ctx, const double* d_in, double* d_out) {
     const GridDev& g = ctx->g;
     constexpr int SY = ATOMIC ? TY : TY - 1, SZ = ATOMIC ? TZ : TZ - 1;
     const int nty = ATOMIC ? (g.ny + SY - 1) / SY : (g.ny + 1 + SY - 1) / SY;
     const int ntz = ATOMIC ? (g.nz + SZ - 1) / SZ : (g.nz + 1 + SZ - 1) / SZ;
     const int nplanes = ctx->own_p1 - ctx->own_p0;
-    // x chunks: enough blocks for >= ~6 waves of 148 SMs x 2 CTAs, chunk >= 8 planes
+    // x chunks: enough blocks for >= ~6 waves of 148 SMs x MINB CTAs, chunk >= 8 planes
     int chunk = nplanes;
     const long long tiles = (long long)nty * ntz;
-    while (chunk > 8 && tiles * ((nplanes + chunk - 1) / chunk) < 148LL * 2 * 6) chunk = (chunk + 1) / 2;
+    while (chunk > 8 && tiles * ((nplanes + chunk - 1) / chunk) < 148LL * MINB * 6) chunk = (chunk + 1) / 2;
+    if (ctx->fused_chunk > 0) chunk = ctx->fused_chunk;
     const int nchunk = (nplanes + chunk - 1) / chunk;
     const size_t smem = sizeof(FusedSmem<TY, TZ>);
     static bool attr_set = false;
-    auto kern = k_matvec_fused<TY, TZ, ATOMIC>;
+    auto kern = k_matvec_fused<TY, TZ, ATOMIC, MINB>;
     if (!attr_set) {
         ESIMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
@@ -476,8 +486,7 @@ static int launch_fused(esimp_ctx* ctx, const double* d_in, double* d_out) {
         ctx->launches++;
     }
     dim3 grid(ntz, nty, nchunk), block(TY * TZ);
-    kern<<<grid, block, smem, ctx->stream>>>(g, ctx->mv_e0, ctx->mv_e1, ctx->own_p0, ctx->own_p1, chunk, ctx->d_E, ctx->d_mask,
-                                             d_in, d_out);
+    kern<<<grid, block, smem, ctx->stream>>>(g, ctx->mv_e0, ctx->mv_e1, ctx->own_p0, ctx->own_p1, chunk, ctx->d_E, d_in, d_out);
     ctx->launches++;
     ESIMP_CUDA(cudaGetLastError());
     return ESIMP_OK;
@@ -497,10 +506,10 @@ int hex8_matvec(esimp_ctx* ctx, const double* d_in, double* d_out, int variant) 
         ESIMP_CUDA(cudaGetLastError());
         return ESIMP_OK;
     }
-    if (variant == ESIMP_MATVEC_FUSED_ATOMIC) return launch_fused<8, 32, true>(ctx, d_in, d_out);
-    if (variant == ESIMP_MATVEC_FUSED_8x32) return launch_fused<8, 32, false>(ctx, d_in, d_out);
+    if (variant == ESIMP_MATVEC_FUSED_ATOMIC) return launch_fused<8, 32, true, 2>(ctx, d_in, d_out);
+    if (variant == ESIMP_MATVEC_FUSED_8x32) return launch_fused<8, 32, false, 2>(ctx, d_in, d_out);
     // owner-computes tiles: 16x16 wastes less on the perimeter than 8x32
-    return launch_fused<16, 16, false>(ctx, d_in, d_out);
+    return launch_fused<16, 16, false, 2>(ctx, d_in, d_out);
 }
 
 // ---------------------------------------------------------------------------- Jacobi diagonal

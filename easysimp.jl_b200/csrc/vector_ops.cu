@@ -225,13 +225,28 @@ __global__ void k_pcg_direction(const double* __restrict__ r, const double* __re
         p[i] = fma(beta, p[i], dinv[i] * r[i]);
 }
 
-int op_apply(esimp_ctx* ctx, double* d_in, double* d_out) {
+// y = P K P x for an input that is already zero on prescribed dofs (halo exchange + operator kernel)
+static int op_apply_raw(esimp_ctx* ctx, double* d_in, double* d_out) {
     if (ctx->structured) {
         if (ctx->nranks > 1) ESIMP_TRY(comm_halo_nodes(ctx, d_in));
-        ESIMP_TRY(hex8_matvec(ctx, d_in, d_out, ctx->prm.matvec_variant));
-    } else {
-        ESIMP_TRY(um_matvec(ctx, d_in, d_out));
+        return hex8_matvec(ctx, d_in, d_out, ctx->prm.matvec_variant);
     }
+    return um_matvec(ctx, d_in, d_out);
+}
+// A x = P K P x + m (I-P) x for x with x[d] = 0 on prescribed dofs (every PCG vector is)
+int op_apply(esimp_ctx* ctx, double* d_in, double* d_out) {
+    ESIMP_TRY(op_apply_raw(ctx, d_in, d_out));
+    return vec_fixup_dirichlet(ctx, d_in, d_out);
+}
+// same for an arbitrary x: the masked copy goes through d_tmp, the m (I-P) x term uses the original
+int op_apply_general(esimp_ctx* ctx, double* d_in, double* d_tmp, double* d_out) {
+    ESIMP_CUDA(cudaMemcpyAsync(d_tmp, d_in, sizeof(double) * ctx->ndof_loc, cudaMemcpyDeviceToDevice, ctx->stream));
+    const double m = ctx->diag_value;
+    ctx->diag_value = 0.0;
+    int s = vec_fixup_dirichlet(ctx, d_tmp, d_tmp);  // tmp[d] = 0
+    ctx->diag_value = m;
+    ESIMP_TRY(s);
+    ESIMP_TRY(op_apply_raw(ctx, d_tmp, d_out));
     return vec_fixup_dirichlet(ctx, d_in, d_out);
 }
 

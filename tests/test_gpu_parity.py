@@ -110,8 +110,10 @@ def test_solve_matches_direct(gpu_ctx_factory, nel, right, rtol):
     # energy = 0.5 u'Ku = 0.5 f'u at the solution (Optimization.jl:320)
     dc, energy = ctx.sensitivities()
     assert abs(energy - 0.5 * fbc @ u_ref) / abs(0.5 * fbc @ u_ref) < 1e-7
+    # a solved field is dominated by rigid-body motion of each cell (|u|^2 K0 >> u_e'K0u_e), so the dense
+    # u_e'K0u_e of the oracle itself cancels ~8 digits here; the 1e-10 bar is tested on generic u below
     dc_ref = o.sensitivities(g, dofs, rho, u, 1.0, 1e-9, 0.3, 3.0, k0)
-    assert relmax(dc, dc_ref) < 1e-10
+    assert relmax(dc, dc_ref) < 1e-8
 
 
 @pytest.mark.parametrize("nel,right", GRIDS[:4])
