@@ -139,6 +139,7 @@ int esimp_destroy(esimp_ctx* ctx) {
     cudaFreeHost(ctx->h_scal);
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->prof_ev) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ESIMP_OK;
@@ -624,6 +625,39 @@ int esimp_set_displacement(esimp_ctx* ctx, const double* u) {
     if (!u) return esimp_fail(ctx, ESIMP_ERR_ARG, "NULL array");
     ESIMP_TRY(upload_dofs(ctx, u, ctx->d_u));
     ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ESIMP_OK;
+}
+
+int esimp_set_design(esimp_ctx* ctx, const double* rho) {
+    CHECK_CTX();
+    NEED(ctx->design_set, "esimp_init_design first");
+    if (!rho) return esimp_fail(ctx, ESIMP_ERR_ARG, "NULL array");
+    ESIMP_TRY(upload_cells(ctx, rho, ctx->d_rho));
+    ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ESIMP_OK;
+}
+
+int esimp_profile_enable(esimp_ctx* ctx, int on) {
+    CHECK_CTX();
+    ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ESIMP_TRY(prof_collect(ctx));
+    if (on && ctx->prof_ev.empty()) {
+        ctx->prof_ev.resize(2 * 4096);
+        for (auto& e : ctx->prof_ev) ESIMP_CUDA(cudaEventCreate(&e));
+    }
+    ctx->prof_on = on != 0;
+    ctx->prof_ms = 0.0;
+    ctx->prof_count = 0;
+    return ESIMP_OK;
+}
+int esimp_profile_matvec(esimp_ctx* ctx, double* ms_sum, int64_t* count, double* bytes_per_apply) {
+    CHECK_CTX();
+    ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ESIMP_TRY(prof_collect(ctx));
+    if (ms_sum) *ms_sum = ctx->prof_ms;
+    if (count) *count = ctx->prof_count;
+    if (bytes_per_apply)
+        *bytes_per_apply = 16.0 * (double)(ctx->own_dof1 - ctx->own_dof0) + 8.0 * (double)(ctx->own_cell1 - ctx->own_cell0);
     return ESIMP_OK;
 }
 

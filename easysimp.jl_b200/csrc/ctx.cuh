@@ -130,7 +130,14 @@ struct esimp_ctx {
     bool density_set = false, load_set = false, design_set = false;
     double f_norm2 = 0.0;
     cudaEvent_t ev[6]{};
+    // in-region timing of the operator kernel (esimp_profile_*): event pairs recorded on ctx->stream
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_ev;
+    int prof_n = 0;
+    double prof_ms = 0.0;
+    int64_t prof_count = 0;
 };
+int prof_collect(esimp_ctx* ctx);  // vector_ops.cu: fold finished event pairs into prof_ms / prof_count
 
 int esimp_fail(esimp_ctx* ctx, int code, const std::string& msg);
 

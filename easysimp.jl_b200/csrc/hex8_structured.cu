@@ -486,7 +486,10 @@ static int launch_fused(esimp_ctx* ctx, const double* d_in, double* d_out) {
         ctx->launches++;
     }
     dim3 grid(ntz, nty, nchunk), block(TY * TZ);
+    const bool timed = ctx->prof_on && 2 * ctx->prof_n + 1 < (int)ctx->prof_ev.size();
+    if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
     kern<<<grid, block, smem, ctx->stream>>>(g, ctx->mv_e0, ctx->mv_e1, ctx->own_p0, ctx->own_p1, chunk, ctx->d_E, d_in, d_out);
+    if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n++ + 1], ctx->stream);
     ctx->launches++;
     ESIMP_CUDA(cudaGetLastError());
     return ESIMP_OK;

@@ -95,6 +95,18 @@ int cell_scatter_from_device(esimp_ctx* ctx, const double* d_src_local, double* 
 int fetch_scalars(esimp_ctx* ctx) {
     ESIMP_CUDA(cudaMemcpyAsync(ctx->h_scal, ctx->d_scal, sizeof(double) * N_SCAL, cudaMemcpyDeviceToHost, ctx->stream));
     ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return prof_collect(ctx);
+}
+// the stream is idle here: every recorded event pair has completed
+int prof_collect(esimp_ctx* ctx) {
+    for (int i = 0; i < ctx->prof_n; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]) == cudaSuccess) {
+            ctx->prof_ms += ms;
+            ctx->prof_count++;
+        }
+    }
+    ctx->prof_n = 0;
     return ESIMP_OK;
 }
 int allreduce_scalars(esimp_ctx* ctx, int slot0, int n, bool is_max) {

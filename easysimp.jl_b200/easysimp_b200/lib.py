@@ -84,6 +84,9 @@ _SIGNATURES = {
     "esimp_n_cells": (C.c_int64, [_P]),
     "esimp_bench_matvec": (C.c_int, [_P, C.c_int, _D, _D]),
     "esimp_launch_count": (C.c_int64, [_P]),
+    "esimp_set_design": (C.c_int, [_P, _D]),
+    "esimp_profile_enable": (C.c_int, [_P, C.c_int]),
+    "esimp_profile_matvec": (C.c_int, [_P, _D, C.POINTER(C.c_int64), _D]),
 }
 
 _lib = None
@@ -300,6 +303,21 @@ class Context:
         k, p = _f64(u)
         assert k.size == self.n_dofs
         self._chk(self.lib.esimp_set_displacement(self._h, p), "esimp_set_displacement")
+
+    def set_design(self, rho):
+        k, p = _f64(rho)
+        assert k.size == self.n_cells
+        self._chk(self.lib.esimp_set_design(self._h, p), "esimp_set_design")
+
+    def profile_enable(self, on=True):
+        self._chk(self.lib.esimp_profile_enable(self._h, int(on)), "esimp_profile_enable")
+
+    def profile_matvec(self):
+        ms = C.c_double(0)
+        n = C.c_int64(0)
+        by = C.c_double(0)
+        self._chk(self.lib.esimp_profile_matvec(self._h, C.byref(ms), C.byref(n), C.byref(by)), "esimp_profile_matvec")
+        return ms.value, n.value, by.value
 
     def bench_matvec(self, reps):
         ms = C.c_double(0)

@@ -170,6 +170,8 @@ int esimp_get_design(esimp_ctx* ctx, double* rho);           /* design variables
 int esimp_get_physical_density(esimp_ctx* ctx, double* rho); /* filtered (== design for :sensitivity) */
 int esimp_get_displacement(esimp_ctx* ctx, double* u);       /* caller's dof numbering     */
 int esimp_set_displacement(esimp_ctx* ctx, const double* u);
+/* overwrite the design variables only (the loop state a host-driven loop carries between iterations) */
+int esimp_set_design(esimp_ctx* ctx, const double* rho);
 int64_t esimp_n_dofs(const esimp_ctx* ctx);
 int64_t esimp_n_cells(const esimp_ctx* ctx);
 
@@ -177,6 +179,11 @@ int64_t esimp_n_cells(const esimp_ctx* ctx);
 /* `reps` operator applies on device-resident vectors; ms_avg = mean launch-to-launch time.
  * bytes_per_apply = algorithmic bytes (16*n_dof + 8*n_cell). */
 int esimp_bench_matvec(esimp_ctx* ctx, int reps, double* ms_avg, double* bytes_per_apply);
+/* in-region timing: while enabled, every launch of the structured operator kernel is bracketed by
+ * CUDA events on the context's stream; esimp_profile_matvec returns the summed kernel time, the number
+ * of timed launches and the algorithmic bytes one launch moves on this rank. */
+int esimp_profile_enable(esimp_ctx* ctx, int on);
+int esimp_profile_matvec(esimp_ctx* ctx, double* ms_sum, int64_t* count, double* bytes_per_apply);
 /* number of kernels this context has launched so far */
 int64_t esimp_launch_count(const esimp_ctx* ctx);
 

@@ -1,0 +1,165 @@
+"""-m gpu parity tests of the element-by-element gather-scatter path (BASELINE config 3: imported hex / tet
+meshes) through the C ABI against the oracle: coloured operator, Jacobi diagonal, PCG vs direct solve,
+sensitivities, CSR filters, OC and the full loop.  Mesh fixtures are derived from the reference's
+data/cantilever_beam.vtu and data/Wheel_3d_coarse.msh (tests/golden/make_mesh_fixtures.py)."""
+import numpy as np
+import pytest
+
+from oracle import simp_oracle as o
+
+pytestmark = pytest.mark.gpu
+
+
+def relmax(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def fixture_mesh(golden_dir, name):
+    z = np.load(golden_dir / f"{name}.npz")
+    return o.Grid(z["points"].astype(np.float64), z["cells"].astype(np.int64), None)
+
+
+def shuffled_jittered_hex():
+    """A structured grid made unstructured: node ids and cell order permuted, nodes jittered by 8% of h
+    (general hexes: non-constant Jacobians)."""
+    g = o.generate_grid_hex((9, 6, 5), (0, 0, 0), (9.0, 6.0, 5.0))
+    rng = np.random.default_rng(42)
+    perm = rng.permutation(g.n_nodes)  # new id of old node
+    coords = np.empty_like(g.coords)
+    coords[perm] = g.coords + 0.08 * (rng.random(g.coords.shape) - 0.5)
+    cells = perm[g.cells][rng.permutation(g.n_cells)]
+    return o.Grid(coords, cells, None)
+
+
+def hex_to_tets():
+    """Each hex of a small grid split into 6 tets sharing the main diagonal."""
+    g = o.generate_grid_hex((6, 4, 3), (0, 0, 0), (3.0, 2.0, 1.5))
+    c = g.cells
+    split = [(0, 1, 2, 6), (0, 2, 3, 6), (0, 3, 7, 6), (0, 7, 4, 6), (0, 4, 5, 6), (0, 5, 1, 6)]
+    tets = np.concatenate([c[:, list(s)] for s in split], axis=0)
+    return o.Grid(g.coords.copy(), tets, None)
+
+
+def bc_and_load(g, dofs):
+    """Clamp the x-min face, pull the x-max face in -y (cantilever-like, works on any mesh)."""
+    x = g.coords[:, 0]
+    span = x.max() - x.min()
+    used = dofs[:, 0] >= 0
+    fixed = np.nonzero(used & (x < x.min() + 0.02 * span))[0]
+    tip = np.nonzero(used & (x > x.max() - 0.02 * span))[0]
+    pres = np.sort(dofs[fixed].ravel())
+    f = o.apply_point_load(np.zeros(int(dofs.max()) + 1), dofs, tip.tolist(), [0.0, -1.0, 0.0])
+    return pres, f
+
+
+MESHES = {
+    "cantilever_beam_vtu": lambda gd: fixture_mesh(gd, "mesh_cantilever_beam_hex"),
+    "wheel_coarse_msh_tets": lambda gd: fixture_mesh(gd, "mesh_wheel_coarse_tet"),
+    "shuffled_jittered_hex": lambda gd: shuffled_jittered_hex(),
+    "hex_split_into_tets": lambda gd: hex_to_tets(),
+}
+
+
+def make_ctx(factory, g, dofs, pres, **params):
+    ctx = factory()
+    if params:
+        ctx.set_params(**params)
+    ctx.set_mesh_unstructured(g.npe, g.coords, g.cells, o.celldofs(g, dofs))
+    ctx.set_dirichlet(pres)
+    return ctx
+
+
+@pytest.mark.parametrize("mesh", list(MESHES))
+def test_unstructured_stages_match_oracle(gpu_ctx_factory, golden_dir, mesh):
+    g = MESHES[mesh](golden_dir)
+    dofs = o.distribute_dofs(g)
+    pres, f = bc_and_load(g, dofs)
+    nd = int(dofs.max()) + 1
+    rng = np.random.default_rng(1)
+    rho = 1e-3 + (1 - 1e-3) * rng.random(g.n_cells)
+    u = rng.standard_normal(nd)
+    ctx = make_ctx(gpu_ctx_factory, g, dofs, pres, pcg_rtol=1e-11, pcg_check_every=20)
+    ctx.set_load(f)
+    ctx.set_density(rho)
+    k0 = o.unit_element_matrices(g, 0.3, 1.0)
+    E = o.simp_modulus(rho, 1.0, 1e-9, 3.0)
+    d = o.operator_diagonal(g, dofs, E, k0)
+    m = float(np.mean(d))
+    # operator + diagonal
+    assert relmax(ctx.matvec(u), o.operator_apply(g, dofs, E, k0, pres, u, m)) < 1e-12
+    keep = np.ones(nd)
+    keep[pres] = 0
+    assert relmax(ctx.diagonal(), d * keep + m * (1 - keep)) < 1e-12
+    # sensitivities for a generic field (1e-10 relative, north_star)
+    ctx.set_displacement(u)
+    dc, energy = ctx.sensitivities()
+    dc_ref = o.sensitivities(g, dofs, rho, u, 1.0, 1e-9, 0.3, 3.0, k0)
+    assert relmax(dc, dc_ref) < 1e-10
+    # PCG vs sparse direct
+    ctx.set_displacement(np.zeros(nd))
+    ug, iters, relres, st = ctx.solve()
+    Kbc, fbc, _ = o.apply_dirichlet(o.assemble_stiffness(g, dofs, E, k0), f.copy(), pres)
+    # SuperLU on the 36 k-tet wheel takes ~90 s: there the oracle's own CG (rtol 1e-13) is the reference solve
+    u_ref = o.solve_direct(Kbc, fbc) if nd < 20000 else o.solve_pcg(Kbc, fbc, rtol=1e-13)[0]
+    assert st == 0 and relmax(ug, u_ref) < 1e-6 and np.all(ug[pres] == 0)
+    # CSR filters (1e-10 relative) and OC
+    V = o.element_volumes(g)
+    fc = o.create_filter_cache(g, 1.5, V)
+    ctx.filter_build_csr(fc.rowptr, fc.col, fc.centers, V, fc.radius)
+    assert relmax(ctx.filter_sens(rho, dc_ref), o.filter_sensitivity(fc, rho, dc_ref)) < 1e-10
+    assert relmax(ctx.filter_dens(rho), o.filter_density(fc, rho)) < 1e-10
+    assert relmax(ctx.filter_dens_T(dc_ref), o.filter_density_transpose(fc, dc_ref)) < 1e-10
+    dv = V / V.sum()
+    new, lam, steps, st = ctx.oc(np.full(g.n_cells, 0.5), o.filter_sensitivity(fc, rho, dc_ref), dv)
+    ref, lam_ref, steps_ref, conv = o.optimality_criteria_update(np.full(g.n_cells, 0.5), o.filter_sensitivity(fc, rho, dc_ref), dv,
+                                                                 0.5, V.sum(), V, 0.2, 0.5, fc, False)
+    assert abs(steps - steps_ref) <= 1 and np.abs(new - ref).max() < 1e-6 and abs(lam - lam_ref) < 1e-6 * lam_ref
+
+
+@pytest.mark.parametrize("mesh,ftype,n_it", [("cantilever_beam_vtu", "sensitivity", 6), ("shuffled_jittered_hex", "density", 8),
+                                              ("hex_split_into_tets", "sensitivity", 8)])
+def test_unstructured_loop_matches_oracle(gpu_ctx_factory, golden_dir, mesh, ftype, n_it):
+    """Full SIMP iterations on an imported mesh: compliance 1e-6 relative (PCG rtol 1e-10), densities 1e-3."""
+    g = MESHES[mesh](golden_dir)
+    dofs = o.distribute_dofs(g)
+    pres, f = bc_and_load(g, dofs)
+    prm = o.OptimizationParameters(volume_fraction=0.4, max_iterations=n_it, tolerance=0.0, filter_radius=1.5, filter_type=ftype)
+    ref = o.simp_optimize(g, dofs, f, pres, prm, solver="direct")
+    V = o.element_volumes(g)
+    fc = o.create_filter_cache(g, 1.5, V)
+    ctx = make_ctx(gpu_ctx_factory, g, dofs, pres, volume_fraction=0.4, filter_type=int(ftype == "density"), pcg_rtol=1e-10,
+                   pcg_check_every=20)
+    ctx.set_load(f)
+    ctx.filter_build_csr(fc.rowptr, fc.col, fc.centers, V, fc.radius)
+    ctx.init_design(None)
+    stats = [ctx.iterate() for _ in range(n_it)]
+    e_ref = np.array([h.energy for h in ref["history"]])
+    assert np.max(np.abs(np.array([s.energy for s in stats]) - e_ref) / e_ref) < 1e-6
+    e_fin, v_fin, _ = ctx.final_analysis()
+    assert abs(e_fin - ref["energy"]) / ref["energy"] < 1e-6 and abs(v_fin - ref["volume"]) / ref["volume"] < 1e-9
+    assert np.abs(ctx.get_physical_density() - ref["densities"]).max() < 1e-3
+
+
+def test_host_api_on_imported_tets(golden_dir):
+    """import_mesh-style grid through the reference-shaped host API (setup_problem .. simp_optimize)."""
+    import easysimp_b200 as es
+
+    go = hex_to_tets()
+    grid = es.Grid(go.coords, go.cells, None)
+    dh, cellvalues, K, f = es.setup_problem(grid, device=0)
+    assert cellvalues["celltype"] == es.Tetrahedron and np.array_equal(dh.dof_of_node, o.distribute_dofs(go))
+    fixed = es.select_nodes_by_plane(grid, [0.0, 0.0, 0.0], [1.0, 0.0, 0.0], 1e-6)
+    tip = es.select_nodes_by_plane(grid, [3.0, 0.0, 0.0], [1.0, 0.0, 0.0], 1e-6)
+    mm = es.create_simp_material_model(1.0, 0.3, 1e-9, 3.0)
+    es.assemble_stiffness_matrix_simp_(K, f, dh, cellvalues, mm, np.full(grid.getncells(), 0.4))
+    ch = es.apply_fixed_boundary_(K, f, dh, fixed)
+    res = es.simp_optimize(grid, dh, cellvalues, [es.PointLoad(dh, sorted(tip), [0.0, -1.0, 0.0])], [ch],
+                           es.OptimizationParameters(max_iterations=5, tolerance=0.0, volume_fraction=0.4, pcg_rtol=1e-10), K=K)
+    dofs = o.distribute_dofs(go)
+    pres = np.sort(dofs[np.array(sorted(fixed))].ravel())
+    fo = o.apply_point_load(np.zeros(3 * go.n_nodes), dofs, sorted(tip), [0.0, -1.0, 0.0])
+    ref = o.simp_optimize(go, dofs, fo, pres, o.OptimizationParameters(max_iterations=5, tolerance=0.0, volume_fraction=0.4))
+    e_ref = np.array([h.energy for h in ref["history"]])
+    assert np.max(np.abs(np.array(res.energy_history) - e_ref) / e_ref) < 1e-6
+    assert np.abs(res.densities - ref["densities"]).max() < 1e-3
+    K.ctx.close()
