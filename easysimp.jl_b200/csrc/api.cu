@@ -134,6 +134,7 @@ int esimp_destroy(esimp_ctx* ctx) {
     comm_destroy(ctx);
     free_mesh_state(ctx);
     cudaFree(ctx->d_partial);
+    cudaFree(ctx->d_partial_mv);
     cudaFree(ctx->d_ticket);
     cudaFree(ctx->d_scal);
     cudaFreeHost(ctx->h_scal);

@@ -124,6 +124,8 @@ struct esimp_ctx {
     int64_t stage_cap = 0;
     // reductions
     double* d_partial = nullptr;    // [8][RED_BLOCKS]
+    double* d_partial_mv = nullptr; // one partial per CTA of the fused operator (fused <p,q>)
+    long long partial_mv_cap = 0;
     unsigned int* d_ticket = nullptr;
     double* d_scal = nullptr;       // device scalars (see SC_* in vector_ops.cu)
     double* h_scal = nullptr;       // pinned mirror
@@ -142,20 +144,22 @@ int prof_collect(esimp_ctx* ctx);  // vector_ops.cu: fold finished event pairs i
 int esimp_fail(esimp_ctx* ctx, int code, const std::string& msg);
 
 // ------------------------------------------------------------------ launch geometry helpers
-constexpr int RED_BLOCKS = 148 * 4;  // persistent grid-stride grids: 4 CTAs of 256 per SM
+constexpr int RED_BLOCKS = 148 * 8;  // persistent grid-stride grids: 8 CTAs of 256 per SM (full occupancy)
 constexpr int RED_THREADS = 256;
 constexpr int N_SCAL = 32;
 
 // device scalar slots
 enum {
-    SC_PQ = 0, SC_RZ0 = 1, SC_RZ1 = 2, SC_RR = 3, SC_FF = 4, SC_VOL = 5, SC_ENERGY = 6, SC_CHANGE = 7,
-    SC_GRAY = 8, SC_MAXU = 9, SC_DIAGSUM = 10, SC_TMP0 = 11, SC_TMP1 = 12, SC_TMP2 = 13
+    // PCG: <p,q>; two ping-pong pairs (<r,z>, <r,r>) so that one 2-double allreduce serves both; <f,f>
+    SC_PQ = 0, SC_RZ0 = 1, SC_RR0 = 2, SC_RZ1 = 3, SC_RR1 = 4, SC_FF = 5, SC_VOL = 6, SC_ENERGY = 7, SC_CHANGE = 8,
+    SC_GRAY = 9, SC_MAXU = 10, SC_DIAGSUM = 11, SC_TMP0 = 12, SC_TMP1 = 13, SC_TMP2 = 14
 };
 
 // ------------------------------------------------------------------ module entry points
 // hex8_structured.cu
 int hex8_upload_constants(esimp_ctx* ctx);
-int hex8_matvec(esimp_ctx* ctx, const double* d_in, double* d_out, int variant);
+int hex8_matvec(esimp_ctx* ctx, const double* d_in, double* d_out, int variant, int dot_slot = -1);
+bool hex8_matvec_fuses_dot(const esimp_ctx* ctx);
 int hex8_diagonal(esimp_ctx* ctx);                 // fills d_dinv with 1/diag, sets diag_value
 int hex8_sens_energy(esimp_ctx* ctx);              // d_dc (owned), SC_ENERGY
 // vector_ops.cu
@@ -218,7 +222,16 @@ struct RedOut {
     double* p[NV];
 };
 template <int NV, bool IS_MAX>
+__device__ __forceinline__ void grid_reduce_idx(double (&v)[NV], double* partial, unsigned int* ticket, const RedOut<NV>& out,
+                                                unsigned int bid, unsigned int nblk);
+template <int NV, bool IS_MAX>
 __device__ __forceinline__ void grid_reduce(double (&v)[NV], double* partial, unsigned int* ticket, const RedOut<NV>& out) {
+    grid_reduce_idx<NV, IS_MAX>(v, partial, ticket, out, blockIdx.x, gridDim.x);
+}
+// partial: [NV][nblk]; bid = linear CTA id; every thread of every CTA must call it
+template <int NV, bool IS_MAX>
+__device__ __forceinline__ void grid_reduce_idx(double (&v)[NV], double* partial, unsigned int* ticket, const RedOut<NV>& out,
+                                                unsigned int bid, unsigned int nblk) {
     __shared__ double s_red[NV][32];
     __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
@@ -233,13 +246,13 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double* partial, un
         for (int i = 0; i < NV; ++i) {
             double w = lane < nwarp ? s_red[i][lane] : (IS_MAX ? -1.0e300 : 0.0);
             w = IS_MAX ? warp_max(w) : warp_sum(w);
-            if (lane == 0) partial[(size_t)i * gridDim.x + blockIdx.x] = w;
+            if (lane == 0) partial[(size_t)i * nblk + bid] = w;
         }
     }
     if (threadIdx.x == 0) {
         __threadfence();
         unsigned int t = atomicAdd(ticket, 1u);
-        s_last = (t == gridDim.x - 1);
+        s_last = (t == nblk - 1);
     }
     __syncthreads();
     if (s_last) {
@@ -247,8 +260,8 @@ __device__ __forceinline__ void grid_reduce(double (&v)[NV], double* partial, un
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             double acc = IS_MAX ? -1.0e300 : 0.0;
-            for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) {
-                double w = __ldcg(&partial[(size_t)i * gridDim.x + b]);
+            for (unsigned int b = threadIdx.x; b < nblk; b += blockDim.x) {
+                double w = __ldcg(&partial[(size_t)i * nblk + b]);
                 acc = IS_MAX ? fmax(acc, w) : acc + w;
             }
             acc = IS_MAX ? warp_max(acc) : warp_sum(acc);

@@ -284,10 +284,11 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-template <int TY, int TZ, bool ATOMIC, int MINB>
+template <int TY, int TZ, bool ATOMIC, int MINB, bool DOT>
 __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le0, int le1, int ps0, int ps1, int chunk,
                                                                const double* __restrict__ E, const double* __restrict__ u,
-                                                               double* __restrict__ y) {
+                                                               double* __restrict__ y, double* partial, unsigned int* ticket,
+                                                               RedOut<1> dot_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     FusedSmem<TY, TZ>& sm = *reinterpret_cast<FusedSmem<TY, TZ>*>(smem_raw);
     const int tid = threadIdx.x;
@@ -306,7 +307,8 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
     // node planes this block owns and the cell layers that touch them
     const int P0 = ps0 + blockIdx.z * chunk, P1 = min(P0 + chunk, ps1);
     const int Lstart = max(P0 - g.e2p - 1, le0), Lend = min(P1 - g.e2p, le1);
-    if (Lstart >= Lend) return;
+    double pq[1] = {0.0};  // <in, out> over the nodes this thread stores (fused PCG dot product)
+    if (Lstart < Lend) {   // always true for a valid slab (every owned plane touches a cell layer)
     const int nsteps = Lend - Lstart;
     const int pl0 = Lstart + g.e2p;  // first node plane read
     const long long plane = g.plane, plane3 = 3 * g.plane;
@@ -353,13 +355,14 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
         sm.out[buf][2][c][ty + 1][tz + 1] = y11;  // -> node (ty+1, tz+1)
     };
     // combine the corner contributions of the plane py points at, write the node totals, advance py
-    auto flush_plane = [&](int buf, bool store, const double (&c00)[3]) {
+    auto flush_plane = [&](int buf, int ring, bool store, const double (&c00)[3]) {
         if (store) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 double s = c00[c] + sm.out[buf][0][c][ty + 1][tz] + sm.out[buf][1][c][ty][tz + 1] + sm.out[buf][2][c][ty][tz];
                 if (own_store) {
                     py[c * plane] = s;
+                    if (DOT) pq[0] = fma(s, sm.in[ring][c][ty][tz], pq[0]);  // the input plane is still in its ring slot
                 } else if (ATOMIC && node_ok) {
                     atomicAdd(&py[c * plane], s);
                 }
@@ -425,7 +428,7 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
         }
         cp_async_wait<1>();  // plane pl0+it+2 has landed (only the newest group may be pending)
         __syncthreads();
-        flush_plane(BUF, lp >= P0 && lp < P1, c00);
+        flush_plane(BUF, it & 3, lp >= P0 && lp < P1, c00);
         issue_plane(it + 4);  // into the slot of plane pl0+it, which nobody reads any more
         ++lp;
     };
@@ -446,7 +449,13 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
             put_corners(nsteps & 1, c, y01, y10, y11);
         }
         __syncthreads();
-        flush_plane(nsteps & 1, lp >= P0 && lp < P1, c00);
+        flush_plane(nsteps & 1, nsteps & 3, lp >= P0 && lp < P1, c00);
+    }
+    }  // Lstart < Lend
+    if (DOT) {
+        const unsigned int nblk = gridDim.x * gridDim.y * gridDim.z;
+        const unsigned int bid = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+        grid_reduce_idx<1, false>(pq, partial, ticket, dot_out, bid, nblk);
     }
 }
 
@@ -461,8 +470,8 @@ __global__ void k_zero_perimeter(GridDev g, int ps0, int ps1, double* __restrict
     }
 }
 
-template <int TY, int TZ, bool ATOMIC, int MINB>
-static int launch_fused(esimp_ctx* ctx, const double* d_in, double* d_out) {
+template <int TY, int TZ, bool ATOMIC, int MINB, bool DOT>
+static int launch_fused_t(esimp_ctx* ctx, const double* d_in, double* d_out, int dot_slot) {
     const GridDev& g = ctx->g;
     constexpr int SY = ATOMIC ? TY : TY - 1, SZ = ATOMIC ? TZ : TZ - 1;
     const int nty = ATOMIC ? (g.ny + SY - 1) / SY : (g.ny + 1 + SY - 1) / SY;
@@ -476,7 +485,7 @@ static int launch_fused(esimp_ctx* ctx, const double* d_in, double* d_out) {
     const int nchunk = (nplanes + chunk - 1) / chunk;
     const size_t smem = sizeof(FusedSmem<TY, TZ>);
     static bool attr_set = false;
-    auto kern = k_matvec_fused<TY, TZ, ATOMIC, MINB>;
+    auto kern = k_matvec_fused<TY, TZ, ATOMIC, MINB, DOT>;
     if (!attr_set) {
         ESIMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
@@ -486,17 +495,36 @@ static int launch_fused(esimp_ctx* ctx, const double* d_in, double* d_out) {
         ctx->launches++;
     }
     dim3 grid(ntz, nty, nchunk), block(TY * TZ);
+    const long long nblk = (long long)ntz * nty * nchunk;
+    if (DOT && nblk > ctx->partial_mv_cap) {
+        cudaFree(ctx->d_partial_mv);
+        ESIMP_CUDA(cudaMalloc(&ctx->d_partial_mv, sizeof(double) * nblk));
+        ctx->partial_mv_cap = nblk;
+    }
+    RedOut<1> dot_out{{ctx->d_scal + (DOT ? dot_slot : 0)}};
     const bool timed = ctx->prof_on && 2 * ctx->prof_n + 1 < (int)ctx->prof_ev.size();
     if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
-    kern<<<grid, block, smem, ctx->stream>>>(g, ctx->mv_e0, ctx->mv_e1, ctx->own_p0, ctx->own_p1, chunk, ctx->d_E, d_in, d_out);
+    kern<<<grid, block, smem, ctx->stream>>>(g, ctx->mv_e0, ctx->mv_e1, ctx->own_p0, ctx->own_p1, chunk, ctx->d_E, d_in, d_out,
+                                             ctx->d_partial_mv, ctx->d_ticket + 2, dot_out);
     if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n++ + 1], ctx->stream);
     ctx->launches++;
     ESIMP_CUDA(cudaGetLastError());
     return ESIMP_OK;
 }
 
-// y = P K P u (prescribed rows are fixed up by vec_fixup_dirichlet)
-int hex8_matvec(esimp_ctx* ctx, const double* d_in, double* d_out, int variant) {
+template <int TY, int TZ, bool ATOMIC, int MINB>
+static int launch_fused(esimp_ctx* ctx, const double* d_in, double* d_out, int dot_slot) {
+    return dot_slot >= 0 ? launch_fused_t<TY, TZ, ATOMIC, MINB, true>(ctx, d_in, d_out, dot_slot)
+                         : launch_fused_t<TY, TZ, ATOMIC, MINB, false>(ctx, d_in, d_out, -1);
+}
+
+bool hex8_matvec_fuses_dot(const esimp_ctx* ctx) {
+    return ctx->structured && ctx->prm.matvec_variant != ESIMP_MATVEC_DENSE_ATOMIC;
+}
+
+// y = P K P u (prescribed rows are fixed up by vec_fixup_dirichlet).  dot_slot >= 0: also leaves <u, y> over the
+// owned dofs in d_scal[dot_slot] (fused into the operator's store; structured fused variants only)
+int hex8_matvec(esimp_ctx* ctx, const double* d_in, double* d_out, int variant, int dot_slot) {
     ESIMP_TRY(hex8_upload_constants(ctx));
     const GridDev& g = ctx->g;
     if (variant == ESIMP_MATVEC_AUTO) variant = ESIMP_MATVEC_FUSED;
@@ -509,10 +537,10 @@ int hex8_matvec(esimp_ctx* ctx, const double* d_in, double* d_out, int variant) 
         ESIMP_CUDA(cudaGetLastError());
         return ESIMP_OK;
     }
-    if (variant == ESIMP_MATVEC_FUSED_ATOMIC) return launch_fused<8, 32, true, 2>(ctx, d_in, d_out);
-    if (variant == ESIMP_MATVEC_FUSED_8x32) return launch_fused<8, 32, false, 2>(ctx, d_in, d_out);
+    if (variant == ESIMP_MATVEC_FUSED_ATOMIC) return launch_fused<8, 32, true, 2>(ctx, d_in, d_out, dot_slot);
+    if (variant == ESIMP_MATVEC_FUSED_8x32) return launch_fused<8, 32, false, 2>(ctx, d_in, d_out, dot_slot);
     // owner-computes tiles: 16x16 wastes less on the perimeter than 8x32
-    return launch_fused<16, 16, false, 2>(ctx, d_in, d_out);
+    return launch_fused<16, 16, false, 2>(ctx, d_in, d_out, dot_slot);
 }
 
 // ---------------------------------------------------------------------------- Jacobi diagonal

@@ -212,38 +212,97 @@ __global__ void k_pcg_init(const double* __restrict__ f, const double* __restric
     }
     grid_reduce<3, false>(acc, partial, ticket, out);
 }
-// alpha = rz/pq;  x += alpha p;  r -= alpha q;  rz_new = <r, Dinv r>;  rr = <r,r>
-__global__ void k_pcg_update(const double* __restrict__ p, const double* __restrict__ q, const double* __restrict__ dinv,
-                             double* __restrict__ x, double* __restrict__ r, long long i0, long long i1,
-                             const double* __restrict__ s_rz, const double* __restrict__ s_pq, double* partial,
-                             unsigned int* ticket, RedOut<2> out) {
+// Streaming helper: [i0, i1) with 128-bit accesses.  All vectors share one index space and their base
+// pointers are 256-byte aligned (cudaMalloc), so one alignment peel serves every array.
+template <typename F2, typename F1>
+__device__ __forceinline__ void stream_pairs(long long i0, long long i1, F2 f2, F1 f1) {
+    long long a0 = (i0 + 1) & ~1LL, a1 = i1 & ~1LL;
+    if (a0 > i1) a0 = i1;
+    if (a1 < a0) a1 = a0;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (long long)gridDim.x * blockDim.x;
+    if (tid == 0 && a0 > i0) f1(i0);
+    if (tid == nth - 1 && i1 > a1) f1(a1);
+    const long long v1 = a1 >> 1;
+    long long v = (a0 >> 1) + tid;
+    for (; v + nth < v1; v += 2 * nth) {  // two independent 16-byte transactions per array in flight
+        f2(v);
+        f2(v + nth);
+    }
+    if (v < v1) f2(v);
+}
+#define D2(ptr) reinterpret_cast<double2*>(ptr)
+#define CD2(ptr) reinterpret_cast<const double2*>(ptr)
+
+// alpha = rz/pq;  r -= alpha q;  rz_new = <r, Dinv r>;  rr = <r,r>          (24 B read + 8 B written per dof)
+__global__ void __launch_bounds__(256, 4) k_pcg_update(const double* __restrict__ q, const double* __restrict__ dinv,
+                                                    double* __restrict__ r, long long i0, long long i1,
+                                                    const double* __restrict__ s_rz, const double* __restrict__ s_pq,
+                                                    double* partial, unsigned int* ticket, RedOut<2> out) {
     const double alpha = *s_rz / *s_pq;
     double acc[2] = {0.0, 0.0};
-    for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (long long)gridDim.x * blockDim.x) {
-        x[i] = fma(alpha, p[i], x[i]);
-        double ri = fma(-alpha, q[i], r[i]);
-        r[i] = ri;
-        acc[0] = fma(ri * dinv[i], ri, acc[0]);
-        acc[1] = fma(ri, ri, acc[1]);
-    }
+    stream_pairs(
+        i0, i1,
+        [&](long long v) {
+            double2 qi = CD2(q)[v], di = CD2(dinv)[v], ri = D2(r)[v];
+            ri.x = fma(-alpha, qi.x, ri.x);
+            ri.y = fma(-alpha, qi.y, ri.y);
+            D2(r)[v] = ri;
+            acc[0] = fma(ri.x * di.x, ri.x, acc[0]);
+            acc[0] = fma(ri.y * di.y, ri.y, acc[0]);
+            acc[1] = fma(ri.x, ri.x, acc[1]);
+            acc[1] = fma(ri.y, ri.y, acc[1]);
+        },
+        [&](long long i) {
+            double ri = fma(-alpha, q[i], r[i]);
+            r[i] = ri;
+            acc[0] = fma(ri * dinv[i], ri, acc[0]);
+            acc[1] = fma(ri, ri, acc[1]);
+        });
     grid_reduce<2, false>(acc, partial, ticket, out);
 }
-// beta = rz_new/rz_old;  p = Dinv r + beta p
-__global__ void k_pcg_direction(const double* __restrict__ r, const double* __restrict__ dinv, double* __restrict__ p,
-                                long long i0, long long i1, const double* __restrict__ s_rz_new,
-                                const double* __restrict__ s_rz_old) {
-    const double beta = *s_rz_new / *s_rz_old;
-    for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (long long)gridDim.x * blockDim.x)
-        p[i] = fma(beta, p[i], dinv[i] * r[i]);
+// x += alpha p (deferred from the update: p is read here anyway);  beta = rz_new/rz_old;  p = Dinv r + beta p
+//                                                                      (32 B read + 16 B written per dof)
+__global__ void __launch_bounds__(256, 4) k_pcg_direction(const double* __restrict__ r, const double* __restrict__ dinv,
+                                                       double* __restrict__ p, double* __restrict__ x, long long i0, long long i1,
+                                                       const double* __restrict__ s_rz_new, const double* __restrict__ s_rz_old,
+                                                       const double* __restrict__ s_pq) {
+    const double beta = *s_rz_new / *s_rz_old, alpha = *s_rz_old / *s_pq;
+    stream_pairs(
+        i0, i1,
+        [&](long long v) {
+            double2 pi = D2(p)[v], xi = D2(x)[v], ri = CD2(r)[v], di = CD2(dinv)[v];
+            xi.x = fma(alpha, pi.x, xi.x);
+            xi.y = fma(alpha, pi.y, xi.y);
+            pi.x = fma(beta, pi.x, di.x * ri.x);
+            pi.y = fma(beta, pi.y, di.y * ri.y);
+            D2(x)[v] = xi;
+            D2(p)[v] = pi;
+        },
+        [&](long long i) {
+            const double pi = p[i];
+            x[i] = fma(alpha, pi, x[i]);
+            p[i] = fma(beta, pi, dinv[i] * r[i]);
+        });
 }
 
 // y = P K P x for an input that is already zero on prescribed dofs (halo exchange + operator kernel)
-static int op_apply_raw(esimp_ctx* ctx, double* d_in, double* d_out) {
+static int op_apply_raw(esimp_ctx* ctx, double* d_in, double* d_out, int dot_slot = -1) {
     if (ctx->structured) {
         if (ctx->nranks > 1) ESIMP_TRY(comm_halo_nodes(ctx, d_in));
-        return hex8_matvec(ctx, d_in, d_out, ctx->prm.matvec_variant);
+        return hex8_matvec(ctx, d_in, d_out, ctx->prm.matvec_variant, dot_slot);
     }
     return um_matvec(ctx, d_in, d_out);
+}
+int op_apply(esimp_ctx* ctx, double* d_in, double* d_out);
+// q = A p and <p,q> in d_scal[slot]: fused into the operator's store where the kernel supports it
+static int op_apply_dot(esimp_ctx* ctx, double* d_in, double* d_out, int slot) {
+    if (hex8_matvec_fuses_dot(ctx)) {
+        ESIMP_TRY(op_apply_raw(ctx, d_in, d_out, slot));
+        ESIMP_TRY(vec_fixup_dirichlet(ctx, d_in, d_out));  // in[d] = 0 there, so <in,out> is unaffected
+        return allreduce_scalars(ctx, slot, 1, false);
+    }
+    ESIMP_TRY(op_apply(ctx, d_in, d_out));
+    return vec_dot(ctx, d_in, d_out, slot);
 }
 // A x = P K P x + m (I-P) x for x with x[d] = 0 on prescribed dofs (every PCG vector is)
 int op_apply(esimp_ctx* ctx, double* d_in, double* d_out) {
@@ -267,21 +326,22 @@ int op_apply_general(esimp_ctx* ctx, double* d_in, double* d_tmp, double* d_out)
 int pcg_solve(esimp_ctx* ctx, int* iters, double* relres) {
     const long long i0 = ctx->own_dof0, i1 = ctx->own_dof1;
     double* S = ctx->d_scal;
+    static const int RZ[2] = {SC_RZ0, SC_RZ1}, RR[2] = {SC_RR0, SC_RR1};
     // r = f - A u
     ESIMP_TRY(op_apply(ctx, ctx->d_u, ctx->d_q));
     {
-        RedOut<3> out{{S + SC_RZ0, S + SC_RR, S + SC_FF}};
+        RedOut<3> out{{S + RZ[0], S + RR[0], S + SC_FF}};
         LAUNCH_STREAM(k_pcg_init, ctx->d_f, ctx->d_q, ctx->d_dinv, ctx->d_r, ctx->d_p, i0, i1, ctx->d_partial, ctx->d_ticket, out);
         if (ctx->nranks > 1) {
-            ESIMP_TRY(comm_allreduce(ctx, S + SC_RZ0, 1, false));
-            ESIMP_TRY(comm_allreduce(ctx, S + SC_RR, 2, false));  // RR, FF adjacent
+            ESIMP_TRY(comm_allreduce(ctx, S + RZ[0], 2, false));  // <r,z>, <r,r> adjacent
+            ESIMP_TRY(comm_allreduce(ctx, S + SC_FF, 1, false));
         }
     }
     ESIMP_TRY(fetch_scalars(ctx));
     const double ff = ctx->h_scal[SC_FF];
     ctx->f_norm2 = ff;
     const double tol2 = ctx->prm.pcg_rtol * ctx->prm.pcg_rtol * ff;
-    double rr = ctx->h_scal[SC_RR];
+    double rr = ctx->h_scal[RR[0]];
     int it = 0;
     const int every = ctx->prm.pcg_check_every > 0 ? ctx->prm.pcg_check_every : 1;
     int status = ESIMP_OK;
@@ -290,23 +350,18 @@ int pcg_solve(esimp_ctx* ctx, int* iters, double* relres) {
         rr = 0.0;
     }
     while (rr > tol2 && it < ctx->prm.pcg_maxit) {
-        const int cur = it & 1;  // rz slot holding <r,z> of the current residual
-        ESIMP_TRY(op_apply(ctx, ctx->d_p, ctx->d_q));
-        ESIMP_TRY(vec_dot(ctx, ctx->d_p, ctx->d_q, SC_PQ));
+        const int cur = it & 1, nxt = cur ^ 1;  // pair holding <r,z>, <r,r> of the current / next residual
+        ESIMP_TRY(op_apply_dot(ctx, ctx->d_p, ctx->d_q, SC_PQ));
         {
-            RedOut<2> out{{S + SC_RZ0 + (cur ^ 1), S + SC_RR}};
-            LAUNCH_STREAM(k_pcg_update, ctx->d_p, ctx->d_q, ctx->d_dinv, ctx->d_u, ctx->d_r, i0, i1, S + SC_RZ0 + cur, S + SC_PQ,
-                          ctx->d_partial, ctx->d_ticket, out);
-            if (ctx->nranks > 1) {
-                ESIMP_TRY(comm_allreduce(ctx, S + SC_RZ0 + (cur ^ 1), 1, false));
-                ESIMP_TRY(comm_allreduce(ctx, S + SC_RR, 1, false));
-            }
+            RedOut<2> out{{S + RZ[nxt], S + RR[nxt]}};
+            LAUNCH_STREAM(k_pcg_update, ctx->d_q, ctx->d_dinv, ctx->d_r, i0, i1, S + RZ[cur], S + SC_PQ, ctx->d_partial, ctx->d_ticket, out);
+            if (ctx->nranks > 1) ESIMP_TRY(comm_allreduce(ctx, S + RZ[nxt], 2, false));
         }
-        LAUNCH_STREAM(k_pcg_direction, ctx->d_r, ctx->d_dinv, ctx->d_p, i0, i1, S + SC_RZ0 + (cur ^ 1), S + SC_RZ0 + cur);
+        LAUNCH_STREAM(k_pcg_direction, ctx->d_r, ctx->d_dinv, ctx->d_p, ctx->d_u, i0, i1, S + RZ[nxt], S + RZ[cur], S + SC_PQ);
         ++it;
         if (it % every == 0 || it >= ctx->prm.pcg_maxit) {
             ESIMP_TRY(fetch_scalars(ctx));
-            rr = ctx->h_scal[SC_RR];
+            rr = ctx->h_scal[RR[nxt]];
             if (!(rr == rr)) return esimp_fail(ctx, ESIMP_ERR_STATE, "PCG breakdown: residual is NaN");
         }
     }
