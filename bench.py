@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--filter-radius", type=float, default=1.5)
     ap.add_argument("--volfrac", type=float, default=0.5)
     ap.add_argument("--variant", type=int, default=0)
+    ap.add_argument("--precond", default="gmg", choices=["jacobi", "gmg"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -170,7 +171,9 @@ def workload_config(args, nel, pcg_iters, pcg_note):
     nx, ny, nz = nel
     return {"workload": f"hex cantilever {nx}x{ny}x{nz} unit cubes, {nx * ny * nz} cells, {3 * (nx + 1) * (ny + 1) * (nz + 1)} dofs",
             "volume_fraction": args.volfrac, "p": 3.0, "E0": 1.0, "Emin": 1e-9, "nu": 0.3, "filter": "sensitivity",
-            "filter_radius": args.filter_radius, "move_limit": 0.2, "damping": 0.5, "solver": "Jacobi-PCG fp64, warm start",
+            "filter_radius": args.filter_radius, "move_limit": 0.2, "damping": 0.5,
+            "solver": ("CG fp64 + geometric-multigrid V(2,2) Chebyshev-Jacobi preconditioner" if args.precond == "gmg" and args.impl == "b200"
+                       else "Jacobi-PCG fp64") + ", warm start",
             "pcg_rtol": args.pcg_rtol, "mean_pcg_iters_per_step": pcg_iters, "pcg_iters_source": pcg_note,
             "partition": f"x-slabs over {args.gpus} GPU(s)", "l2": "inputs_larger_than_l2 (813 MB per vector vs 126 MB L2)"}
 
@@ -196,7 +199,7 @@ def run_b200(args):
     pres, f = cantilever(nel)
     ctx = es.Context(local)
     ctx.set_params(volume_fraction=args.volfrac, filter_radius=args.filter_radius, pcg_rtol=args.pcg_rtol, pcg_maxit=200000,
-                   pcg_check_every=50, matvec_variant=args.variant, warm_start=1)
+                   pcg_check_every=50, matvec_variant=args.variant, warm_start=1, precond=int(args.precond == "gmg"))
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -280,7 +283,9 @@ def run_b200(args):
                "history": [{"energy": s.energy, "change": s.change, "pcg_iters": s.pcg_iters, "pcg_relres": s.pcg_relres, "oc_steps": s.oc_steps}
                            for s in stats + timed]}
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_sample(nel, args, pcg_iters)
+            # the CPU port is Jacobi-PCG: scale its sample with ITS iteration count (measured once with the same
+            # Jacobi-PCG on the GPU, bench_calibration.json), not with this arm's multigrid count
+            cb = cpu_sample(nel, args, pcg_iters if args.precond == "jacobi" else calibrated_pcg_iters(args.workload, args.pcg_rtol)[0])
             out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         print(json.dumps(out), flush=True)
     ctx.close()

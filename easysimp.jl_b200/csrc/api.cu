@@ -56,6 +56,8 @@ static void free_mesh_state(esimp_ctx* ctx) {
     ctx->stage_cap = 0;
     ctx->n_fixed = 0;
     um_free(ctx);
+    mg_free(ctx);
+    ctx->prescribed_nc.clear();
     ctx->structured = ctx->unstructured = false;
     ctx->filter_ready = ctx->density_set = ctx->load_set = ctx->design_set = false;
     ctx->k0_valid = false;
@@ -89,6 +91,7 @@ int esimp_default_params(esimp_params* p) {
     p->pcg_check_every = 25;
     p->matvec_variant = ESIMP_MATVEC_AUTO;
     p->warm_start = 1;
+    p->precond = ESIMP_PRECOND_JACOBI;
     return ESIMP_OK;
 }
 
@@ -109,6 +112,9 @@ int esimp_create(esimp_ctx** out, int device) {
     ctx->device = device;
     esimp_default_params(&ctx->prm);
     if (const char* e = getenv("ESIMP_FUSED_CHUNK")) ctx->fused_chunk = atoi(e);
+    if (const char* e = getenv("ESIMP_MG_NU")) ctx->mg_nu = std::max(1, atoi(e));
+    if (const char* e = getenv("ESIMP_MG_COARSE_ITS")) ctx->mg_coarse_its = std::max(1, atoi(e));
+    if (const char* e = getenv("ESIMP_MG_RATIO")) ctx->mg_ratio = std::max(1.5, atof(e));
     auto bail = [&](const char* what) {
         std::string msg = std::string(what) + ": " + cudaGetErrorString(cudaGetLastError());
         delete ctx;
@@ -170,6 +176,7 @@ int esimp_set_params(esimp_ctx* ctx, const esimp_params* p) {
     if (!p) return esimp_fail(ctx, ESIMP_ERR_ARG, "params is NULL");
     if (!(p->nu > -1.0 && p->nu < 0.5) || !(p->E0 > 0) || !(p->p >= 1.0)) return esimp_fail(ctx, ESIMP_ERR_ARG, "invalid material parameters");
     bool nu_changed = p->nu != ctx->prm.nu;
+    if (p->precond != ESIMP_PRECOND_JACOBI && p->precond != ESIMP_PRECOND_GMG) return esimp_fail(ctx, ESIMP_ERR_ARG, "unknown preconditioner");
     bool r_changed = p->filter_radius != ctx->prm.filter_radius;
     ctx->prm = *p;
     if (nu_changed) {
@@ -266,6 +273,7 @@ int esimp_set_dirichlet(esimp_ctx* ctx, const int64_t* dofs, int64_t n) {
         ESIMP_CUDA(cudaMemcpy(ctx->d_mask, mask.data(), mask.size(), cudaMemcpyHostToDevice));
     } else {
         const GridDev& g = ctx->g;
+        ctx->prescribed_nc.clear();
         std::vector<uint8_t> mask((size_t)g.NPX * g.plane, 0);
         std::vector<int64_t> inv;  // caller dof -> 3*node + c
         if (ctx->d_dof_of_node) {
@@ -280,6 +288,7 @@ int esimp_set_dirichlet(esimp_ctx* ctx, const int64_t* dofs, int64_t n) {
             if (d < 0 || d >= ctx->n_dofs_global) return esimp_fail(ctx, ESIMP_ERR_ARG, "prescribed dof out of range");
             int64_t q = inv.empty() ? d : inv[d];
             if (q < 0) return esimp_fail(ctx, ESIMP_ERR_ARG, "prescribed dof not in dof_of_node");
+            ctx->prescribed_nc.push_back(q);
             int c = (int)(q % 3);
             int64_t nref = q / 3;
             int gi = (int)(nref % (g.nx + 1));
@@ -293,6 +302,7 @@ int esimp_set_dirichlet(esimp_ctx* ctx, const int64_t* dofs, int64_t n) {
         }
         ESIMP_CUDA(cudaMemcpy(ctx->d_mask, mask.data(), mask.size(), cudaMemcpyHostToDevice));
     }
+    ctx->bc_version++;
     ctx->n_fixed = (int64_t)fixed.size();
     ESIMP_TRY(dev_alloc(ctx, &ctx->d_fixed, ctx->n_fixed, false));
     if (ctx->n_fixed) ESIMP_CUDA(cudaMemcpy(ctx->d_fixed, fixed.data(), sizeof(int64_t) * ctx->n_fixed, cudaMemcpyHostToDevice));
@@ -358,6 +368,7 @@ static int prepare_operator(esimp_ctx* ctx) {
         ESIMP_TRY(hex8_diagonal(ctx));
     else
         ESIMP_TRY(um_diagonal(ctx));
+    if (ctx->prm.precond == ESIMP_PRECOND_GMG && ctx->structured) ESIMP_TRY(mg_setup(ctx));
     ctx->density_set = true;
     return ESIMP_OK;
 }
@@ -404,6 +415,7 @@ static int solve_internal(esimp_ctx* ctx, int* iters, double* relres) {
     NEED(ctx->load_set, "esimp_set_load first");
     if (!ctx->prm.warm_start) ESIMP_CUDA(cudaMemsetAsync(ctx->d_u, 0, sizeof(double) * ctx->ndof_loc, ctx->stream));
     ESIMP_TRY(mask_rhs_and_guess(ctx));
+    if (ctx->prm.precond == ESIMP_PRECOND_GMG && ctx->structured) return pcg_solve_mg(ctx, iters, relres);
     return pcg_solve(ctx, iters, relres);
 }
 
@@ -634,6 +646,9 @@ int esimp_set_design(esimp_ctx* ctx, const double* rho) {
     NEED(ctx->design_set, "esimp_init_design first");
     if (!rho) return esimp_fail(ctx, ESIMP_ERR_ARG, "NULL array");
     ESIMP_TRY(upload_cells(ctx, rho, ctx->d_rho));
+    // multi-rank: the caller's array is authoritative only on the cells this rank owns (esimp_get_design fills
+    // nothing else), so the ghost layers are refreshed from their owners
+    if (ctx->nranks > 1 && ctx->structured) ESIMP_TRY(comm_halo_cells(ctx, ctx->d_rho));
     ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));
     return ESIMP_OK;
 }

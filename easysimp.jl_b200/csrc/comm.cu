@@ -108,38 +108,43 @@ int comm_allreduce(esimp_ctx* ctx, double* d_buf, int n, bool is_max) {
 
 // Send my first / last OWNED node plane to the left / right neighbour, receive their planes into my
 // ghost planes.  A plane is 3*plane contiguous doubles ([lp][c][y][z] layout): no packing.
-int comm_halo_nodes(esimp_ctx* ctx, double* v) {
+int comm_halo_nodes_lv(esimp_ctx* ctx, const GridDev& g, int own_p0, int own_p1, bool has_left, bool has_right, double* v) {
     if (ctx->nranks <= 1) return ESIMP_OK;
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
-    const size_t np = (size_t)3 * ctx->g.plane;
+    const size_t np = (size_t)3 * g.plane;
     ESIMP_NCCL(g_nccl.GroupStart());
-    if (ctx->has_left) {
-        ESIMP_NCCL(g_nccl.Send(v + (size_t)ctx->own_p0 * np, np, ncclDouble, ctx->rank - 1, comm, ctx->stream));
+    if (has_left) {
+        ESIMP_NCCL(g_nccl.Send(v + (size_t)own_p0 * np, np, ncclDouble, ctx->rank - 1, comm, ctx->stream));
         ESIMP_NCCL(g_nccl.Recv(v, np, ncclDouble, ctx->rank - 1, comm, ctx->stream));
     }
-    if (ctx->has_right) {
-        ESIMP_NCCL(g_nccl.Send(v + (size_t)(ctx->own_p1 - 1) * np, np, ncclDouble, ctx->rank + 1, comm, ctx->stream));
-        ESIMP_NCCL(g_nccl.Recv(v + (size_t)(ctx->g.NPX - 1) * np, np, ncclDouble, ctx->rank + 1, comm, ctx->stream));
+    if (has_right) {
+        ESIMP_NCCL(g_nccl.Send(v + (size_t)(own_p1 - 1) * np, np, ncclDouble, ctx->rank + 1, comm, ctx->stream));
+        ESIMP_NCCL(g_nccl.Recv(v + (size_t)(g.NPX - 1) * np, np, ncclDouble, ctx->rank + 1, comm, ctx->stream));
     }
     ESIMP_NCCL(g_nccl.GroupEnd());
     return ESIMP_OK;
 }
+int comm_halo_nodes(esimp_ctx* ctx, double* v) {
+    return comm_halo_nodes_lv(ctx, ctx->g, ctx->own_p0, ctx->own_p1, ctx->has_left, ctx->has_right, v);
+}
 
-// halo_e cell layers each way (rho, dc for the filter; E for the redundant interface layer)
-int comm_halo_cells(esimp_ctx* ctx, double* a) {
+// `depth` cell layers each way (rho, dc for the filter; E for the redundant interface layer)
+int comm_halo_cells_lv(esimp_ctx* ctx, const GridDev& g, int own_e0, int own_e1, int depth, bool has_left, bool has_right, double* a) {
     if (ctx->nranks <= 1) return ESIMP_OK;
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
-    const size_t nl = (size_t)ctx->halo_e * ctx->g.eplane;
+    const size_t nl = (size_t)depth * g.eplane;
     ESIMP_NCCL(g_nccl.GroupStart());
-    if (ctx->has_left) {
-        ESIMP_NCCL(g_nccl.Send(a + (size_t)ctx->own_e0 * ctx->g.eplane, nl, ncclDouble, ctx->rank - 1, comm, ctx->stream));
-        ESIMP_NCCL(g_nccl.Recv(a, nl, ncclDouble, ctx->rank - 1, comm, ctx->stream));
+    if (has_left) {
+        ESIMP_NCCL(g_nccl.Send(a + (size_t)own_e0 * g.eplane, nl, ncclDouble, ctx->rank - 1, comm, ctx->stream));
+        ESIMP_NCCL(g_nccl.Recv(a + (size_t)(own_e0 - depth) * g.eplane, nl, ncclDouble, ctx->rank - 1, comm, ctx->stream));
     }
-    if (ctx->has_right) {
-        ESIMP_NCCL(g_nccl.Send(a + (size_t)(ctx->own_e1 - ctx->halo_e) * ctx->g.eplane, nl, ncclDouble, ctx->rank + 1, comm,
-                               ctx->stream));
-        ESIMP_NCCL(g_nccl.Recv(a + (size_t)ctx->own_e1 * ctx->g.eplane, nl, ncclDouble, ctx->rank + 1, comm, ctx->stream));
+    if (has_right) {
+        ESIMP_NCCL(g_nccl.Send(a + (size_t)(own_e1 - depth) * g.eplane, nl, ncclDouble, ctx->rank + 1, comm, ctx->stream));
+        ESIMP_NCCL(g_nccl.Recv(a + (size_t)own_e1 * g.eplane, nl, ncclDouble, ctx->rank + 1, comm, ctx->stream));
     }
     ESIMP_NCCL(g_nccl.GroupEnd());
     return ESIMP_OK;
+}
+int comm_halo_cells(esimp_ctx* ctx, double* a) {
+    return comm_halo_cells_lv(ctx, ctx->g, ctx->own_e0, ctx->own_e1, ctx->halo_e, ctx->has_left, ctx->has_right, a);
 }

@@ -52,6 +52,29 @@ struct GridDev {
     }
 };
 
+// what the structured operator needs to know about one grid level (fine grid or a multigrid level)
+struct OpView {
+    GridDev g;
+    int own_p0, own_p1, mv_e0, mv_e1;
+    const double* E;
+    const uint8_t* mask;
+};
+
+// one level of the geometric multigrid hierarchy (level 0 aliases the context's fine-grid arrays)
+struct MGLevel {
+    OpView vw{};
+    bool has_left = false, has_right = false;
+    long long ndof_loc = 0, ncell_loc = 0, own_dof0 = 0, own_dof1 = 0, own_cell0 = 0, own_cell1 = 0, n_dofs_global = 0;
+    double* d_E = nullptr;
+    uint8_t* d_mask = nullptr;
+    long long* d_fixed = nullptr;
+    long long n_fixed = 0;
+    double* d_dinv = nullptr;
+    double diag_value = 1.0, lmax = 4.0;
+    double *d_r = nullptr, *d_z = nullptr, *d_d = nullptr, *d_q = nullptr;  // rhs, correction, Chebyshev direction, A z
+    bool owns = false;
+};
+
 struct UnstructuredMesh {
     int npe = 0;            // 8 or 4
     int64_t n_cells = 0, n_nodes = 0, n_dofs = 0;
@@ -98,6 +121,11 @@ struct esimp_ctx {
     int64_t own_cell0 = 0, own_cell1 = 0; // owned cell range
     int64_t* d_dof_of_node = nullptr;     // caller numbering (global, 3*n_nodes) or null
     UnstructuredMesh um;
+    std::vector<MGLevel> mg;            // geometric multigrid hierarchy (precond == GMG)
+    std::vector<int64_t> prescribed_nc;  // prescribed (3*node_ref + comp), kept for the coarse-level masks
+    int bc_version = 0, mg_bc_version = -1;
+    int mg_nu = 2, mg_coarse_its = 40;
+    double mg_ratio = 6.0;
 
     // element matrices (host copies; uploaded to __constant__ on demand)
     double K0[24 * 24];
@@ -160,6 +188,16 @@ enum {
 int hex8_upload_constants(esimp_ctx* ctx);
 int hex8_matvec(esimp_ctx* ctx, const double* d_in, double* d_out, int variant, int dot_slot = -1);
 bool hex8_matvec_fuses_dot(const esimp_ctx* ctx);
+OpView fine_view(const esimp_ctx* ctx);
+int hex8_matvec_view(esimp_ctx* ctx, const OpView& vw, const double* d_in, double* d_out, int variant, int dot_slot);
+int hex8_diagonal_view(esimp_ctx* ctx, const OpView& vw, double* dinv, long long n_dofs_global, double* diag_value);
+// multigrid.cu
+int mg_setup(esimp_ctx* ctx);          // build / refresh the hierarchy for the current E and mask
+void mg_free(esimp_ctx* ctx);
+int pcg_solve_mg(esimp_ctx* ctx, int* iters, double* relres);
+int fixup_lv(esimp_ctx* ctx, const long long* fixed, long long n_fixed, double m, const double* in, double* out);
+int comm_halo_nodes_lv(esimp_ctx* ctx, const GridDev& g, int own_p0, int own_p1, bool has_left, bool has_right, double* v);
+int comm_halo_cells_lv(esimp_ctx* ctx, const GridDev& g, int own_e0, int own_e1, int depth, bool has_left, bool has_right, double* a);
 int hex8_diagonal(esimp_ctx* ctx);                 // fills d_dinv with 1/diag, sets diag_value
 int hex8_sens_energy(esimp_ctx* ctx);              // d_dc (owned), SC_ENERGY
 // vector_ops.cu

@@ -471,12 +471,12 @@ __global__ void k_zero_perimeter(GridDev g, int ps0, int ps1, double* __restrict
 }
 
 template <int TY, int TZ, bool ATOMIC, int MINB, bool DOT>
-static int launch_fused_t(esimp_ctx* ctx, const double* d_in, double* d_out, int dot_slot) {
-    const GridDev& g = ctx->g;
+static int launch_fused_t(esimp_ctx* ctx, const OpView& vw, const double* d_in, double* d_out, int dot_slot) {
+    const GridDev& g = vw.g;
     constexpr int SY = ATOMIC ? TY : TY - 1, SZ = ATOMIC ? TZ : TZ - 1;
     const int nty = ATOMIC ? (g.ny + SY - 1) / SY : (g.ny + 1 + SY - 1) / SY;
     const int ntz = ATOMIC ? (g.nz + SZ - 1) / SZ : (g.nz + 1 + SZ - 1) / SZ;
-    const int nplanes = ctx->own_p1 - ctx->own_p0;
+    const int nplanes = vw.own_p1 - vw.own_p0;
     // x chunks: enough blocks for >= ~6 waves of 148 SMs x MINB CTAs, chunk >= 8 planes
     int chunk = nplanes;
     const long long tiles = (long long)nty * ntz;
@@ -491,7 +491,7 @@ static int launch_fused_t(esimp_ctx* ctx, const double* d_in, double* d_out, int
         attr_set = true;
     }
     if (ATOMIC) {
-        k_zero_perimeter<TY, TZ><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(g, ctx->own_p0, ctx->own_p1, d_out);
+        k_zero_perimeter<TY, TZ><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(g, vw.own_p0, vw.own_p1, d_out);
         ctx->launches++;
     }
     dim3 grid(ntz, nty, nchunk), block(TY * TZ);
@@ -502,9 +502,10 @@ static int launch_fused_t(esimp_ctx* ctx, const double* d_in, double* d_out, int
         ctx->partial_mv_cap = nblk;
     }
     RedOut<1> dot_out{{ctx->d_scal + (DOT ? dot_slot : 0)}};
-    const bool timed = ctx->prof_on && 2 * ctx->prof_n + 1 < (int)ctx->prof_ev.size();
+    // only fine-grid applies are timed (multigrid levels reuse this kernel on coarser grids)
+    const bool timed = ctx->prof_on && vw.E == ctx->d_E && 2 * ctx->prof_n + 1 < (int)ctx->prof_ev.size();
     if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
-    kern<<<grid, block, smem, ctx->stream>>>(g, ctx->mv_e0, ctx->mv_e1, ctx->own_p0, ctx->own_p1, chunk, ctx->d_E, d_in, d_out,
+    kern<<<grid, block, smem, ctx->stream>>>(g, vw.mv_e0, vw.mv_e1, vw.own_p0, vw.own_p1, chunk, vw.E, d_in, d_out,
                                              ctx->d_partial_mv, ctx->d_ticket + 2, dot_out);
     if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n++ + 1], ctx->stream);
     ctx->launches++;
@@ -513,9 +514,9 @@ static int launch_fused_t(esimp_ctx* ctx, const double* d_in, double* d_out, int
 }
 
 template <int TY, int TZ, bool ATOMIC, int MINB>
-static int launch_fused(esimp_ctx* ctx, const double* d_in, double* d_out, int dot_slot) {
-    return dot_slot >= 0 ? launch_fused_t<TY, TZ, ATOMIC, MINB, true>(ctx, d_in, d_out, dot_slot)
-                         : launch_fused_t<TY, TZ, ATOMIC, MINB, false>(ctx, d_in, d_out, -1);
+static int launch_fused(esimp_ctx* ctx, const OpView& vw, const double* d_in, double* d_out, int dot_slot) {
+    return dot_slot >= 0 ? launch_fused_t<TY, TZ, ATOMIC, MINB, true>(ctx, vw, d_in, d_out, dot_slot)
+                         : launch_fused_t<TY, TZ, ATOMIC, MINB, false>(ctx, vw, d_in, d_out, -1);
 }
 
 bool hex8_matvec_fuses_dot(const esimp_ctx* ctx) {
@@ -524,23 +525,36 @@ bool hex8_matvec_fuses_dot(const esimp_ctx* ctx) {
 
 // y = P K P u (prescribed rows are fixed up by vec_fixup_dirichlet).  dot_slot >= 0: also leaves <u, y> over the
 // owned dofs in d_scal[dot_slot] (fused into the operator's store; structured fused variants only)
-int hex8_matvec(esimp_ctx* ctx, const double* d_in, double* d_out, int variant, int dot_slot) {
+int hex8_matvec_view(esimp_ctx* ctx, const OpView& vw, const double* d_in, double* d_out, int variant, int dot_slot) {
     ESIMP_TRY(hex8_upload_constants(ctx));
-    const GridDev& g = ctx->g;
+    const GridDev& g = vw.g;
     if (variant == ESIMP_MATVEC_AUTO) variant = ESIMP_MATVEC_FUSED;
     if (variant == ESIMP_MATVEC_DENSE_ATOMIC) {
-        ESIMP_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * ctx->ndof_loc, ctx->stream));
-        long long n = (long long)(ctx->mv_e1 - ctx->mv_e0) * g.eplane;
-        k_matvec_dense_atomic<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(g, ctx->mv_e0, ctx->mv_e1, ctx->d_E,
-                                                                                      ctx->d_mask, d_in, d_out);
+        ESIMP_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * 3 * g.NPX * g.plane, ctx->stream));
+        long long n = (long long)(vw.mv_e1 - vw.mv_e0) * g.eplane;
+        k_matvec_dense_atomic<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>(g, vw.mv_e0, vw.mv_e1, vw.E, vw.mask, d_in, d_out);
         ctx->launches++;
         ESIMP_CUDA(cudaGetLastError());
         return ESIMP_OK;
     }
-    if (variant == ESIMP_MATVEC_FUSED_ATOMIC) return launch_fused<8, 32, true, 2>(ctx, d_in, d_out, dot_slot);
-    if (variant == ESIMP_MATVEC_FUSED_8x32) return launch_fused<8, 32, false, 2>(ctx, d_in, d_out, dot_slot);
+    if (variant == ESIMP_MATVEC_FUSED_ATOMIC) return launch_fused<8, 32, true, 2>(ctx, vw, d_in, d_out, dot_slot);
+    if (variant == ESIMP_MATVEC_FUSED_8x32) return launch_fused<8, 32, false, 2>(ctx, vw, d_in, d_out, dot_slot);
     // owner-computes tiles: 16x16 wastes less on the perimeter than 8x32
-    return launch_fused<16, 16, false, 2>(ctx, d_in, d_out, dot_slot);
+    return launch_fused<16, 16, false, 2>(ctx, vw, d_in, d_out, dot_slot);
+}
+OpView fine_view(const esimp_ctx* ctx) {
+    OpView v;
+    v.g = ctx->g;
+    v.own_p0 = ctx->own_p0;
+    v.own_p1 = ctx->own_p1;
+    v.mv_e0 = ctx->mv_e0;
+    v.mv_e1 = ctx->mv_e1;
+    v.E = ctx->d_E;
+    v.mask = ctx->d_mask;
+    return v;
+}
+int hex8_matvec(esimp_ctx* ctx, const double* d_in, double* d_out, int variant, int dot_slot) {
+    return hex8_matvec_view(ctx, fine_view(ctx), d_in, d_out, variant, dot_slot);
 }
 
 // ---------------------------------------------------------------------------- Jacobi diagonal
@@ -595,21 +609,22 @@ __global__ void k_diag_invert(GridDev g, int ps0, int ps1, const uint8_t* __rest
     }
 }
 
-int hex8_diagonal(esimp_ctx* ctx) {
+int hex8_diagonal_view(esimp_ctx* ctx, const OpView& vw, double* dinv, long long n_dofs_global, double* diag_value) {
     ESIMP_TRY(hex8_upload_constants(ctx));
     RedOut<1> out{{ctx->d_scal + SC_DIAGSUM}};
-    k_diag<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(ctx->g, ctx->own_p0, ctx->own_p1, ctx->g.NEX, ctx->d_E, ctx->d_dinv,
-                                                        ctx->d_partial, ctx->d_ticket, out);
+    k_diag<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(vw.g, vw.own_p0, vw.own_p1, vw.g.NEX, vw.E, dinv, ctx->d_partial, ctx->d_ticket, out);
     ctx->launches++;
     ESIMP_CUDA(cudaGetLastError());
     ESIMP_TRY(allreduce_scalars(ctx, SC_DIAGSUM, 1, false));
     ESIMP_TRY(fetch_scalars(ctx));
-    ctx->diag_value = ctx->h_scal[SC_DIAGSUM] / (double)ctx->n_dofs_global;  // mean |diag K| (all entries > 0)
-    k_diag_invert<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(ctx->g, ctx->own_p0, ctx->own_p1, ctx->d_mask, ctx->diag_value,
-                                                               ctx->d_dinv);
+    *diag_value = ctx->h_scal[SC_DIAGSUM] / (double)n_dofs_global;  // mean |diag K| (all entries > 0)
+    k_diag_invert<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(vw.g, vw.own_p0, vw.own_p1, vw.mask, *diag_value, dinv);
     ctx->launches++;
     ESIMP_CUDA(cudaGetLastError());
     return ESIMP_OK;
+}
+int hex8_diagonal(esimp_ctx* ctx) {
+    return hex8_diagonal_view(ctx, fine_view(ctx), ctx->d_dinv, ctx->n_dofs_global, &ctx->diag_value);
 }
 
 // ---------------------------------------------------------------------------- sensitivities + energy

@@ -186,14 +186,17 @@ __global__ void k_fixup(const long long* __restrict__ fixed, long long n, double
         out[d] = m * in[d];
     }
 }
-int vec_fixup_dirichlet(esimp_ctx* ctx, const double* in, double* out) {
-    if (ctx->n_fixed == 0) return ESIMP_OK;
-    int blocks = (int)((ctx->n_fixed + 255) / 256);
+int fixup_lv(esimp_ctx* ctx, const long long* fixed, long long n_fixed, double m, const double* in, double* out) {
+    if (n_fixed == 0) return ESIMP_OK;
+    int blocks = (int)((n_fixed + 255) / 256);
     if (blocks > RED_BLOCKS) blocks = RED_BLOCKS;
-    k_fixup<<<blocks, 256, 0, ctx->stream>>>((const long long*)ctx->d_fixed, ctx->n_fixed, ctx->diag_value, in, out);
+    k_fixup<<<blocks, 256, 0, ctx->stream>>>(fixed, n_fixed, m, in, out);
     ctx->launches++;
     ESIMP_CUDA(cudaGetLastError());
     return ESIMP_OK;
+}
+int vec_fixup_dirichlet(esimp_ctx* ctx, const double* in, double* out) {
+    return fixup_lv(ctx, (const long long*)ctx->d_fixed, ctx->n_fixed, ctx->diag_value, in, out);
 }
 
 // ---------------------------------------------------------------------------- PCG kernels

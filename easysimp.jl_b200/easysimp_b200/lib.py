@@ -28,7 +28,7 @@ class EsimpParams(C.Structure):
         ("volume_fraction", C.c_double), ("move_limit", C.c_double), ("damping", C.c_double),
         ("filter_radius", C.c_double), ("filter_type", C.c_int32), ("pcg_maxit", C.c_int32),
         ("pcg_rtol", C.c_double), ("pcg_check_every", C.c_int32), ("matvec_variant", C.c_int32),
-        ("warm_start", C.c_int32), ("reserved", C.c_int32),
+        ("warm_start", C.c_int32), ("precond", C.c_int32),
     ]
 
 

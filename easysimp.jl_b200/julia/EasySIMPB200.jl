@@ -29,7 +29,7 @@ struct EsimpParams
     volume_fraction::Cdouble; move_limit::Cdouble; damping::Cdouble; filter_radius::Cdouble
     filter_type::Int32; pcg_maxit::Int32
     pcg_rtol::Cdouble
-    pcg_check_every::Int32; matvec_variant::Int32; warm_start::Int32; reserved::Int32
+    pcg_check_every::Int32; matvec_variant::Int32; warm_start::Int32; precond::Int32
 end
 
 # esimp_iter_stats

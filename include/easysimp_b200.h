@@ -54,6 +54,10 @@ extern "C" {
 #define ESIMP_MATVEC_FUSED_ATOMIC 3 /* same, tile perimeters combined with red.global.add.f64           */
 #define ESIMP_MATVEC_FUSED_8x32 4   /* owner-computes with 8x32 (y,z) tiles instead of 16x16            */
 
+/* CG preconditioners */
+#define ESIMP_PRECOND_JACOBI 0 /* diagonal scaling                                                        */
+#define ESIMP_PRECOND_GMG 1    /* geometric multigrid V-cycle on structured grids (csrc/multigrid.cu)     */
+
 typedef struct esimp_ctx esimp_ctx;
 
 /* POD mirror of OptimizationParameters (Optimization.jl:53-123) + solver knobs the
@@ -73,7 +77,7 @@ typedef struct esimp_params {
     int32_t pcg_check_every; /* residual is read back every this many iterations (>=1) */
     int32_t matvec_variant;  /* ESIMP_MATVEC_*                                          */
     int32_t warm_start;      /* 1: PCG starts from the previous displacement            */
-    int32_t reserved;
+    int32_t precond;         /* ESIMP_PRECOND_*                                         */
 } esimp_params;
 
 /* per-iteration scalars the reference logs (OptimizationLogger.jl:26-29,

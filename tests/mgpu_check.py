@@ -80,14 +80,18 @@ def main():
         ctx.close()
 
     # ---- full loops against the golden fixtures
-    for name, problem, rtol in (("c1_cantilever_60x20x4", o.cantilever_problem, 1e-10), ("c2s_4legs_20x10x10", o.four_legs_problem, 1e-10)):
+    for name, problem, rtol, precond in (("c1_cantilever_60x20x4", o.cantilever_problem, 1e-10, 0),
+                                          ("c2s_4legs_20x10x10", o.four_legs_problem, 1e-10, 0),
+                                          ("c1_cantilever_60x20x4", o.cantilever_problem, 1e-10, 1),
+                                          ("c2_4legs_40x20x20", o.four_legs_problem, 1e-10, 1)):
         gz = np.load(ROOT / "tests" / "golden" / f"{name}.npz")
         nel = tuple(int(v) for v in gz["nel"])
         g, dofs, f, pres = problem(nel)
         E0, Emin, nu, p, vf, ratio, move, damp = gz["params"]
         R = ratio * o.estimate_element_size(g)
         ctx = make_ctx(rank, world, local, new_uid(), g, dofs, pres, E0=E0, Emin=Emin, nu=nu, p=p, volume_fraction=vf, move_limit=move,
-                       damping=damp, filter_radius=R, filter_type=int(gz["filter_type"][0]), pcg_rtol=rtol, pcg_check_every=10)
+                       damping=damp, filter_radius=R, filter_type=int(gz["filter_type"][0]), pcg_rtol=rtol, pcg_check_every=10,
+                       precond=precond)
         ctx.set_load(f)
         ctx.filter_build_structured()
         ctx.init_design(None)
@@ -101,7 +105,8 @@ def main():
             v_err = np.max(np.abs(np.array([s.volume for s in stats]) - gz["volume"]) / gz["volume"])
             c_err = np.max(np.abs(np.array([s.change for s in stats]) - gz["change"]))
             d_err = np.abs(dens - gz["final_density"]).max()
-            print(f"[mgpu] {name} on {world} GPUs: compliance rel err {e_err:.2e}, volume {v_err:.2e}, change {c_err:.2e}, "
+            print(f"[mgpu] {name} on {world} GPUs, {'multigrid' if precond else 'Jacobi'}-PCG (mean {np.mean([s.pcg_iters for s in stats]):.0f} its): "
+                  f"compliance rel err {e_err:.2e}, volume {v_err:.2e}, change {c_err:.2e}, "
                   f"final density Linf {d_err:.2e}, final energy rel {abs(e_fin - gz['final_energy'][0]) / gz['final_energy'][0]:.2e}, "
                   f"max|u| {np.abs(disp).max():.4e} vs {stats[-1].max_u:.4e}", flush=True)
             ok &= e_err < 1e-6 and v_err < 1e-9 and d_err < 1e-3 and c_err < 1e-4
