@@ -77,7 +77,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -91,6 +91,8 @@ class ClockSampler:
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        if not self.rows:
+            time.sleep(0.25)  # very short timed regions: wait for at least one sample
         self.proc.terminate()
         self.th.join(timeout=2)
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
@@ -224,10 +226,11 @@ def run_b200(args):
         stats.append(ctx.iterate())
     # ---- timed region: K device-resident iterations
     sampler = ClockSampler(local)
+    sampler.start()  # started before the barrier so that it is already polling when the timed region begins
     ctx.profile_enable(True)
     launches0 = ctx.launch_count
     barrier()
-    sampler.start()
+    sampler.rows.clear()
     t0 = time.perf_counter()
     timed = [ctx.iterate() for _ in range(args.steps)]
     barrier()
