@@ -122,7 +122,7 @@ int esimp_create(esimp_ctx** out, int device) {
     };
     if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice");
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("cudaStreamCreate");
-    if (cudaMalloc(&ctx->d_partial, sizeof(double) * 8 * RED_BLOCKS) != cudaSuccess) return bail("cudaMalloc");
+    if (cudaMalloc(&ctx->d_partial, sizeof(double) * 16 * RED_BLOCKS) != cudaSuccess) return bail("cudaMalloc");
     if (cudaMalloc(&ctx->d_ticket, sizeof(unsigned int) * 8) != cudaSuccess) return bail("cudaMalloc");
     if (cudaMalloc(&ctx->d_scal, sizeof(double) * N_SCAL) != cudaSuccess) return bail("cudaMalloc");
     if (cudaMallocHost(&ctx->h_scal, sizeof(double) * N_SCAL) != cudaSuccess) return bail("cudaMallocHost");

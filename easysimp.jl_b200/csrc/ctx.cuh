@@ -72,6 +72,8 @@ struct MGLevel {
     double* d_dinv = nullptr;
     double diag_value = 1.0, lmax = 4.0;
     double *d_r = nullptr, *d_z = nullptr, *d_d = nullptr, *d_q = nullptr;  // rhs, correction, Chebyshev direction, A z
+    double* d_pi = nullptr;  // power-iteration vector, kept between SIMP iterations (warm start of the lmax estimate)
+    bool pi_valid = false;
     bool owns = false;
 };
 
@@ -151,7 +153,7 @@ struct esimp_ctx {
     double* d_stage = nullptr;  // staging for global host arrays
     int64_t stage_cap = 0;
     // reductions
-    double* d_partial = nullptr;    // [8][RED_BLOCKS]
+    double* d_partial = nullptr;    // [16][RED_BLOCKS]
     double* d_partial_mv = nullptr; // one partial per CTA of the fused operator (fused <p,q>)
     long long partial_mv_cap = 0;
     unsigned int* d_ticket = nullptr;
@@ -180,7 +182,8 @@ constexpr int N_SCAL = 32;
 enum {
     // PCG: <p,q>; two ping-pong pairs (<r,z>, <r,r>) so that one 2-double allreduce serves both; <f,f>
     SC_PQ = 0, SC_RZ0 = 1, SC_RR0 = 2, SC_RZ1 = 3, SC_RR1 = 4, SC_FF = 5, SC_VOL = 6, SC_ENERGY = 7, SC_CHANGE = 8,
-    SC_GRAY = 9, SC_MAXU = 10, SC_DIAGSUM = 11, SC_TMP0 = 12, SC_TMP1 = 13, SC_TMP2 = 14
+    SC_GRAY = 9, SC_MAXU = 10, SC_DIAGSUM = 11, SC_TMP0 = 12, SC_TMP1 = 13, SC_TMP2 = 14,
+    SC_OC0 = 16  // .. SC_OC0 + 14: volumes of the 15 candidate multipliers of one OC multi-section pass
 };
 
 // ------------------------------------------------------------------ module entry points

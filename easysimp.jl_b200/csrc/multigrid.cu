@@ -87,32 +87,28 @@ __global__ void k_restrict(GridDev gf, GridDev gc, int cp0, int cp1, const doubl
     }
 }
 
-// z_f += P z_c on the owned fine nodes (trilinear interpolation), prescribed fine dofs untouched
-__global__ void k_prolong_add(GridDev gf, GridDev gc, int fp0, int fp1, const double* __restrict__ zc,
-                              const uint8_t* __restrict__ maskf, double* __restrict__ zf) {
-    long long n = (long long)(fp1 - fp0) * 3 * gf.plane;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
-        int k = (int)(idx % (gf.nz + 1));
-        long long t = idx / (gf.nz + 1);
-        int j = (int)(t % (gf.ny + 1));
-        t /= (gf.ny + 1);
-        int c = (int)(t % 3);
-        int lp = fp0 + (int)(t / 3);
-        if ((maskf[gf.node(lp, j, k)] >> c) & 1) continue;
+// z_f += P z_c on the owned fine nodes (trilinear interpolation), prescribed fine dofs untouched.
+// Branch-free: along each axis the two parents are index>>1 and (index+1)>>1 (the same node for an even index),
+// each with weight 1/2.  blockIdx.y walks (plane, component), threads walk the (y,z) plane.
+__global__ void __launch_bounds__(256) k_prolong_add(GridDev gf, GridDev gc, int fp0, int fp1, const double* __restrict__ zc,
+                                                     const uint8_t* __restrict__ maskf, double* __restrict__ zf) {
+    const int nyz = (gf.ny + 1) * (gf.nz + 1), nzf = gf.nz + 1;
+    for (int pc = blockIdx.y; pc < (fp1 - fp0) * 3; pc += gridDim.y) {
+        const int lp = fp0 + pc / 3, c = pc % 3;
         const int Gf = gf.gp0 + lp;
-        const int nxp = (Gf & 1) ? 2 : 1, nyp = (j & 1) ? 2 : 1, nzp = (k & 1) ? 2 : 1;
-        double acc = 0.0;
-        for (int a = 0; a < nxp; ++a) {
-            int lpc = ((Gf & 1) ? (Gf - 1) / 2 + a : Gf / 2) - gc.gp0;
-            for (int b = 0; b < nyp; ++b) {
-                int J = (j & 1) ? (j - 1) / 2 + b : j / 2;
-                for (int d = 0; d < nzp; ++d) {
-                    int K = (k & 1) ? (k - 1) / 2 + d : k / 2;
-                    acc += zc[gc.dof(lpc, c, J, K)];
-                }
-            }
+        const int lpc0 = (Gf >> 1) - gc.gp0, lpc1 = ((Gf + 1) >> 1) - gc.gp0;
+        const double* __restrict__ c0 = zc + (long long)(lpc0 * 3 + c) * gc.plane;
+        const double* __restrict__ c1 = zc + (long long)(lpc1 * 3 + c) * gc.plane;
+        double* __restrict__ zrow = zf + (long long)(lp * 3 + c) * gf.plane;
+        const uint8_t* __restrict__ mrow = maskf + (long long)lp * gf.plane;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nyz; i += gridDim.x * blockDim.x) {
+            const int j = i / nzf, k = i - j * nzf;
+            if ((mrow[i] >> c) & 1) continue;
+            const int J0 = (j >> 1) * (gc.nz + 1), J1 = ((j + 1) >> 1) * (gc.nz + 1), K0 = k >> 1, K1 = (k + 1) >> 1;
+            const double s = (c0[J0 + K0] + c0[J0 + K1]) + (c0[J1 + K0] + c0[J1 + K1]) + (c1[J0 + K0] + c1[J0 + K1]) +
+                             (c1[J1 + K0] + c1[J1 + K1]);
+            zrow[i] = fma(0.125, s, zrow[i]);
         }
-        zf[gf.dof(lp, c, j, k)] += acc / (double)(nxp * nyp * nzp);
     }
 }
 
@@ -212,6 +208,7 @@ void mg_free(esimp_ctx* ctx) {
         MGLevel& L = ctx->mg[l];
         cudaFree(L.d_z);
         cudaFree(L.d_d);
+        cudaFree(L.d_pi);
         if (l > 0) {
             cudaFree(L.d_E);
             cudaFree(L.d_mask);
@@ -250,6 +247,7 @@ static int mg_build_levels(esimp_ctx* ctx) {
         L.d_q = ctx->d_q;
         ESIMP_CUDA(cudaMalloc(&L.d_z, sizeof(double) * L.ndof_loc));
         ESIMP_CUDA(cudaMalloc(&L.d_d, sizeof(double) * L.ndof_loc));
+        ESIMP_CUDA(cudaMalloc(&L.d_pi, sizeof(double) * L.ndof_loc));
         ESIMP_CUDA(cudaMemset(L.d_z, 0, sizeof(double) * L.ndof_loc));
         ESIMP_CUDA(cudaMemset(L.d_d, 0, sizeof(double) * L.ndof_loc));
         ctx->mg.push_back(L);
@@ -310,7 +308,7 @@ static int mg_build_levels(esimp_ctx* ctx) {
         ESIMP_CUDA(cudaMalloc(&L.d_fixed, sizeof(long long) * std::max<long long>(L.n_fixed, 1)));
         if (L.n_fixed) ESIMP_CUDA(cudaMemcpy(L.d_fixed, fixed.data(), sizeof(long long) * L.n_fixed, cudaMemcpyHostToDevice));
         ESIMP_CUDA(cudaMalloc(&L.d_E, sizeof(double) * L.ncell_loc));
-        double** vecs[] = {&L.d_dinv, &L.d_r, &L.d_z, &L.d_d, &L.d_q};
+        double** vecs[] = {&L.d_dinv, &L.d_r, &L.d_z, &L.d_d, &L.d_q, &L.d_pi};
         for (double** v : vecs) {
             ESIMP_CUDA(cudaMalloc(v, sizeof(double) * L.ndof_loc));
             ESIMP_CUDA(cudaMemset(*v, 0, sizeof(double) * L.ndof_loc));
@@ -330,7 +328,12 @@ static int mg_apply(esimp_ctx* ctx, MGLevel& L, double* in, double* out, int dot
 
 // lmax(D^-1 A) by power iteration (x in d_z, A x in d_q, D^-1 A x in d_d)
 static int mg_estimate_lmax(esimp_ctx* ctx, MGLevel& L, int iters) {
-    LAUNCH_STREAM(k_pi_init, L.vw.g, L.d_mask, L.d_z, L.own_dof0, L.own_dof1);
+    if (L.pi_valid) {  // warm start from the dominant vector of the previous SIMP iteration: a few steps suffice
+        ESIMP_CUDA(cudaMemcpyAsync(L.d_z, L.d_pi, sizeof(double) * L.ndof_loc, cudaMemcpyDeviceToDevice, ctx->stream));
+        iters = 2;
+    } else {
+        LAUNCH_STREAM(k_pi_init, L.vw.g, L.d_mask, L.d_z, L.own_dof0, L.own_dof1);
+    }
     RedOut<1> out{{ctx->d_scal + SC_TMP0}};
     double lam = 4.0;
     for (int it = 0; it < iters; ++it) {
@@ -343,9 +346,14 @@ static int mg_estimate_lmax(esimp_ctx* ctx, MGLevel& L, int iters) {
     ESIMP_TRY(mg_apply(ctx, L, L.d_z, L.d_q));
     LAUNCH_STREAM(k_pi_scale, L.d_q, L.d_dinv, L.d_d, L.own_dof0, L.own_dof1, ctx->d_partial, ctx->d_ticket, out);
     ESIMP_TRY(allreduce_scalars(ctx, SC_TMP0, 1, false));
+    ESIMP_CUDA(cudaMemcpyAsync(L.d_pi, L.d_z, sizeof(double) * L.ndof_loc, cudaMemcpyDeviceToDevice, ctx->stream));
+    L.pi_valid = true;
     ESIMP_TRY(fetch_scalars(ctx));
     lam = sqrt(ctx->h_scal[SC_TMP0]);
-    if (!(lam > 0.5) || !(lam < 100.0)) lam = 4.0;
+    if (!(lam > 0.5) || !(lam < 100.0)) {
+        lam = 4.0;
+        L.pi_valid = false;
+    }
     L.lmax = 1.1 * lam;
     return ESIMP_OK;
 }
@@ -416,7 +424,13 @@ static int mg_vcycle(esimp_ctx* ctx, int l) {
     LAUNCH_STREAM(k_restrict, L.vw.g, C.vw.g, C.vw.own_p0, C.vw.own_p1, L.d_q, C.d_mask, C.d_r);
     ESIMP_TRY(mg_vcycle(ctx, l + 1));
     if (ctx->nranks > 1) ESIMP_TRY(comm_halo_nodes_lv(ctx, C.vw.g, C.vw.own_p0, C.vw.own_p1, C.has_left, C.has_right, C.d_z));
-    LAUNCH_STREAM(k_prolong_add, L.vw.g, C.vw.g, L.vw.own_p0, L.vw.own_p1, C.d_z, L.d_mask, L.d_z);
+    {
+        const int nyz = (L.vw.g.ny + 1) * (L.vw.g.nz + 1);
+        dim3 grid((unsigned)std::min(64, (nyz + 255) / 256), (unsigned)std::min(65535, (L.vw.own_p1 - L.vw.own_p0) * 3));
+        k_prolong_add<<<grid, 256, 0, ctx->stream>>>(L.vw.g, C.vw.g, L.vw.own_p0, L.vw.own_p1, C.d_z, L.d_mask, L.d_z);
+        ctx->launches++;
+        ESIMP_CUDA(cudaGetLastError());
+    }
     return mg_smooth(ctx, L, ctx->mg_nu, false);
 }
 
