@@ -255,7 +255,7 @@ def run_b200(args):
         for _ in range(args.steps):
             ctx.set_design(rho_host)          # H2D: design densities, 8 B/cell
             s = ctx.iterate()
-            rho_host[:] = ctx.get_design()    # D2H: updated design (the loop state of Optimization.jl:360) + 7 scalars
+            ctx.get_design(out=rho_host)      # D2H into the pinned buffer: updated design (Optimization.jl:360) + 7 scalars
             timed.append(s)
         barrier()
         t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")

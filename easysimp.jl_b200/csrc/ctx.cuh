@@ -126,8 +126,8 @@ struct esimp_ctx {
     std::vector<MGLevel> mg;            // geometric multigrid hierarchy (precond == GMG)
     std::vector<int64_t> prescribed_nc;  // prescribed (3*node_ref + comp), kept for the coarse-level masks
     int bc_version = 0, mg_bc_version = -1;
-    int mg_nu = 2, mg_coarse_its = 40;
-    double mg_ratio = 6.0;
+    int mg_nu = 2, mg_coarse_its = 16;  // tuned on 512x256x256 (scripts/mg_sweep.sh): nu 2, ratio 10 is the fastest
+    double mg_ratio = 10.0;
 
     // element matrices (host copies; uploaded to __constant__ on demand)
     double K0[24 * 24];

@@ -417,7 +417,12 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
         for (int c = 0; c < 3; ++c) {
             double A[4];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
+            // b = 0: w[c][0] is the translation mode, structurally zero (written out so that no 0 -+ x is issued)
+            A[0] = Gpp[c][0] - w[c][1];
+            Gpp[c][0] = w[c][1];
+            Fp[c][0] = Fn[c][0];
+#pragma unroll
+            for (int b = 1; b < 4; ++b) {
                 A[b] = Gpp[c][b] + (w[c][2 * b] - w[c][2 * b + 1]);
                 Gpp[c][b] = w[c][2 * b] + w[c][2 * b + 1];
                 Fp[c][b] = Fn[c][b];

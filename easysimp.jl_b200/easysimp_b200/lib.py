@@ -284,8 +284,11 @@ class Context:
         self._chk(self.lib.esimp_final_analysis(self._h, C.byref(e), C.byref(v), C.byref(it)), "esimp_final_analysis")
         return e.value, v.value, it.value
 
-    def get_design(self):
-        out = np.empty(self.n_cells)
+    def get_design(self, out=None):
+        """`out`: optional caller buffer (e.g. pinned host memory) the library copies into directly."""
+        if out is None:
+            out = np.empty(self.n_cells)
+        assert out.dtype == np.float64 and out.size == self.n_cells and out.flags.c_contiguous
         self._chk(self.lib.esimp_get_design(self._h, out.ctypes.data_as(_D)), "esimp_get_design")
         return out
 
