@@ -396,7 +396,7 @@ int esimp_diagonal(esimp_ctx* ctx, double* d) {
     if (!d) return esimp_fail(ctx, ESIMP_ERR_ARG, "NULL vector");
     ESIMP_TRY(download_dofs(ctx, ctx->d_dinv, d));
     for (int64_t i = 0; i < ctx->n_dofs_global; ++i)
-        if (d[i] != 0.0) d[i] = 1.0 / d[i];
+        d[i] = d[i] != 0.0 ? 1.0 / d[i] : (ctx->structured ? ctx->diag_value : 0.0);  // structured: Dinv is stored as 0 on prescribed dofs
     return ESIMP_OK;
 }
 

@@ -72,6 +72,7 @@ struct MGLevel {
     double* d_dinv = nullptr;
     double diag_value = 1.0, lmax = 4.0;
     double *d_r = nullptr, *d_z = nullptr, *d_d = nullptr, *d_q = nullptr;  // rhs, correction, Chebyshev direction, A z
+    double* d_z2 = nullptr;  // second buffer of the correction: the fused smoother writes z' while neighbours still read z
     double* d_pi = nullptr;  // power-iteration vector, kept between SIMP iterations (warm start of the lmax estimate)
     bool pi_valid = false;
     bool owns = false;
@@ -194,6 +195,9 @@ bool hex8_matvec_fuses_dot(const esimp_ctx* ctx);
 OpView fine_view(const esimp_ctx* ctx);
 int hex8_matvec_view(esimp_ctx* ctx, const OpView& vw, const double* d_in, double* d_out, int variant, int dot_slot);
 int hex8_diagonal_view(esimp_ctx* ctx, const OpView& vw, double* dinv, long long n_dofs_global, double* diag_value);
+int hex8_smooth_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double* z_out, const double* r, const double* dinv,
+                     double* d, double c1, double c2);
+int hex8_resid_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double* res_out, const double* r);
 // multigrid.cu
 int mg_setup(esimp_ctx* ctx);          // build / refresh the hierarchy for the current E and mask
 void mg_free(esimp_ctx* ctx);

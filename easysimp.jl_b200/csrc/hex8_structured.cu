@@ -265,11 +265,13 @@ __global__ void __launch_bounds__(128) k_matvec_dense_atomic(GridDev g, int le0,
 //   perimeter cells are computed twice: deterministic, no zero-fill, ~(1-1/TY)(1-1/TZ) efficient.
 // ATOMIC=true : tiles do not overlap; perimeter nodes are combined with atomicAdd into a y whose
 //   perimeter rows/columns were zeroed first (ncu r1: 2x slower than owner tiles on B200).
-template <int TY, int TZ>
+template <int TY, int TZ, int NF = 0>
 struct FusedSmem {
     double in[4][3][TY + 1][TZ + 1];      // u of a node plane: 4-deep cp.async ring
     double E[4][TY][TZ];                  // modulus of the cell layer consumed together with that plane
     double out[2][3][3][TY + 1][TZ + 1];  // corner contributions c01, c10, c11 at [ty+1][tz+1]; borders stay 0
+    double fz[NF > 0 ? NF : 1][3][TY][TZ];  // fused-update operands (r | r, Dinv, d) of the plane the next flush completes;
+                                            // every thread only touches its own slot, so one buffer and no barrier suffice
 };
 
 // 8-byte asynchronous global->shared copy (LDGSTS); !valid zero-fills the destination
@@ -284,13 +286,29 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-template <int TY, int TZ, bool ATOMIC, int MINB, bool DOT>
+// MODE selects what the store phase does with s = (A u)[dof] on the nodes this thread owns:
+//   FUSE_PLAIN  y = s                                  FUSE_DOT     y = s and <u, y> (PCG)
+//   FUSE_SMOOTH one Chebyshev-Jacobi step of the multigrid smoother with u = z:
+//               v = c1 d + c2 Dinv (r - s);  d = v;  y = z + v      (Dinv is 0 on prescribed dofs)
+//   FUSE_RESID  y = r - s                              (residual that is restricted to the next level)
+// r, Dinv, d of the plane are prefetched into registers at the start of the step (before the FP64 work), so
+// their latency is covered; the operator is FP64-bound, the extra bytes ride for free.
+enum { FUSE_PLAIN = 0, FUSE_DOT = 1, FUSE_SMOOTH = 2, FUSE_RESID = 3 };
+struct FuseArgs {
+    const double* r = nullptr;
+    const double* dinv = nullptr;
+    double* d = nullptr;
+    double c1 = 0.0, c2 = 0.0;
+};
+template <int TY, int TZ, bool ATOMIC, int MINB, int MODE>
 __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le0, int le1, int ps0, int ps1, int chunk,
                                                                const double* __restrict__ E, const double* __restrict__ u,
                                                                double* __restrict__ y, double* partial, unsigned int* ticket,
-                                                               RedOut<1> dot_out) {
+                                                               RedOut<1> dot_out, FuseArgs fa) {
+    constexpr bool DOT = MODE == FUSE_DOT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    FusedSmem<TY, TZ>& sm = *reinterpret_cast<FusedSmem<TY, TZ>*>(smem_raw);
+    constexpr int NF = MODE == FUSE_SMOOTH ? 3 : (MODE == FUSE_RESID ? 1 : 0);
+    FusedSmem<TY, TZ, NF>& sm = *reinterpret_cast<FusedSmem<TY, TZ, NF>*>(smem_raw);
     const int tid = threadIdx.x;
     const int tz = tid % TZ, ty = tid / TZ;
     constexpr int SY = ATOMIC ? TY : TY - 1, SZ = ATOMIC ? TZ : TZ - 1;
@@ -320,6 +338,7 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
     double* py = y + (long long)pl0 * plane3 + (node_ok ? (long long)ey * (g.nz + 1) + ez : 0);
     double* pyh = y + (long long)pl0 * plane3 + (halo_ok ? (long long)hy * (g.nz + 1) + hz : 0);
     const bool own_store = node_ok && ty >= 1 && tz >= 1;
+    long long foff = (long long)pl0 * plane3 + (node_ok ? (long long)ey * (g.nz + 1) + ez : 0);  // same offset as py
 
     // zero the output tiles once (their borders are never written again)
     for (int i = tid; i < 2 * 9 * (TY + 1) * (TZ + 1); i += TY * TZ) (&sm.out[0][0][0][0][0])[i] = 0.0;
@@ -361,8 +380,16 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
             for (int c = 0; c < 3; ++c) {
                 double s = c00[c] + sm.out[buf][0][c][ty + 1][tz] + sm.out[buf][1][c][ty][tz + 1] + sm.out[buf][2][c][ty][tz];
                 if (own_store) {
-                    py[c * plane] = s;
-                    if (DOT) pq[0] = fma(s, sm.in[ring][c][ty][tz], pq[0]);  // the input plane is still in its ring slot
+                    if (MODE == FUSE_SMOOTH) {
+                        const double v = fma(fa.c1, sm.fz[2 % NF][c][ty][tz], fa.c2 * sm.fz[1 % NF][c][ty][tz] * (sm.fz[0][c][ty][tz] - s));
+                        (fa.d + foff)[c * plane] = v;
+                        py[c * plane] = sm.in[ring][c][ty][tz] + v;  // the input plane is still in its ring slot
+                    } else if (MODE == FUSE_RESID) {
+                        py[c * plane] = sm.fz[0][c][ty][tz] - s;
+                    } else {
+                        py[c * plane] = s;
+                    }
+                    if (DOT) pq[0] = fma(s, sm.in[ring][c][ty][tz], pq[0]);
                 } else if (ATOMIC && node_ok) {
                     atomicAdd(&py[c * plane], s);
                 }
@@ -376,9 +403,24 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
         }
         py += plane3;
         pyh += plane3;
+        foff += plane3;
     };
-
+    // asynchronous copy of the fused-update operands of the plane the NEXT flush completes (joins the commit group
+    // of the following issue_plane; FUSE_SMOOTH / FUSE_RESID wait for all groups before the flush)
+    auto issue_fuse = [&](bool store) {
+        if (MODE >= FUSE_SMOOTH && store && own_store) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                cp_async8(&sm.fz[0][c][ty][tz], fa.r + foff + c * plane, true);
+                if (MODE == FUSE_SMOOTH) {
+                    cp_async8(&sm.fz[1 % NF][c][ty][tz], fa.dinv + foff + c * plane, true);
+                    cp_async8(&sm.fz[2 % NF][c][ty][tz], fa.d + foff + c * plane, fa.c1 != 0.0);
+                }
+            }
+        }
+    };
     // ---- prologue: planes pl0 .. pl0+3 in flight, the first two landed
+    issue_fuse(pl0 >= P0 && pl0 < P1);  // operands of the first plane a flush completes (group of plane 0)
     issue_plane(0);
     issue_plane(1);
     issue_plane(2);
@@ -431,11 +473,15 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
             inv2d(A, c00[c], y10, y01, y11);
             put_corners(BUF, c, y01, y10, y11);
         }
-        cp_async_wait<1>();  // plane pl0+it+2 has landed (only the newest group may be pending)
+        if (MODE >= FUSE_SMOOTH)
+            cp_async_wait<0>();  // also the operand tile issued after the previous flush
+        else
+            cp_async_wait<1>();  // plane pl0+it+2 has landed (only the newest group may be pending)
         __syncthreads();
         flush_plane(BUF, it & 3, lp >= P0 && lp < P1, c00);
-        issue_plane(it + 4);  // into the slot of plane pl0+it, which nobody reads any more
         ++lp;
+        issue_fuse(lp >= P0 && lp < P1);  // operands of the next plane, after this thread has consumed its slot
+        issue_plane(it + 4);              // into the slot of plane pl0+it, which nobody reads any more
     };
     int it = 0;
 #pragma unroll 1
@@ -453,6 +499,7 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
             inv2d(Gpp[c], c00[c], y10, y01, y11);
             put_corners(nsteps & 1, c, y01, y10, y11);
         }
+        cp_async_wait<0>();
         __syncthreads();
         flush_plane(nsteps & 1, nsteps & 3, lp >= P0 && lp < P1, c00);
     }
@@ -475,8 +522,9 @@ __global__ void k_zero_perimeter(GridDev g, int ps0, int ps1, double* __restrict
     }
 }
 
-template <int TY, int TZ, bool ATOMIC, int MINB, bool DOT>
-static int launch_fused_t(esimp_ctx* ctx, const OpView& vw, const double* d_in, double* d_out, int dot_slot) {
+template <int TY, int TZ, bool ATOMIC, int MINB, int MODE>
+static int launch_fused_t(esimp_ctx* ctx, const OpView& vw, const double* d_in, double* d_out, int dot_slot, const FuseArgs& fa = FuseArgs()) {
+    constexpr bool DOT = MODE == FUSE_DOT;
     const GridDev& g = vw.g;
     constexpr int SY = ATOMIC ? TY : TY - 1, SZ = ATOMIC ? TZ : TZ - 1;
     const int nty = ATOMIC ? (g.ny + SY - 1) / SY : (g.ny + 1 + SY - 1) / SY;
@@ -488,9 +536,9 @@ static int launch_fused_t(esimp_ctx* ctx, const OpView& vw, const double* d_in, 
     while (chunk > 8 && tiles * ((nplanes + chunk - 1) / chunk) < 148LL * MINB * 6) chunk = (chunk + 1) / 2;
     if (ctx->fused_chunk > 0) chunk = ctx->fused_chunk;
     const int nchunk = (nplanes + chunk - 1) / chunk;
-    const size_t smem = sizeof(FusedSmem<TY, TZ>);
+    const size_t smem = sizeof(FusedSmem<TY, TZ, MODE == FUSE_SMOOTH ? 3 : (MODE == FUSE_RESID ? 1 : 0)>);
     static bool attr_set = false;
-    auto kern = k_matvec_fused<TY, TZ, ATOMIC, MINB, DOT>;
+    auto kern = k_matvec_fused<TY, TZ, ATOMIC, MINB, MODE>;
     if (!attr_set) {
         ESIMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
@@ -508,10 +556,10 @@ static int launch_fused_t(esimp_ctx* ctx, const OpView& vw, const double* d_in, 
     }
     RedOut<1> dot_out{{ctx->d_scal + (DOT ? dot_slot : 0)}};
     // only fine-grid applies are timed (multigrid levels reuse this kernel on coarser grids)
-    const bool timed = ctx->prof_on && vw.E == ctx->d_E && 2 * ctx->prof_n + 1 < (int)ctx->prof_ev.size();
+    const bool timed = ctx->prof_on && MODE <= FUSE_DOT && vw.E == ctx->d_E && 2 * ctx->prof_n + 1 < (int)ctx->prof_ev.size();
     if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
     kern<<<grid, block, smem, ctx->stream>>>(g, vw.mv_e0, vw.mv_e1, vw.own_p0, vw.own_p1, chunk, vw.E, d_in, d_out,
-                                             ctx->d_partial_mv, ctx->d_ticket + 2, dot_out);
+                                             ctx->d_partial_mv, ctx->d_ticket + 2, dot_out, fa);
     if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n++ + 1], ctx->stream);
     ctx->launches++;
     ESIMP_CUDA(cudaGetLastError());
@@ -520,8 +568,8 @@ static int launch_fused_t(esimp_ctx* ctx, const OpView& vw, const double* d_in, 
 
 template <int TY, int TZ, bool ATOMIC, int MINB>
 static int launch_fused(esimp_ctx* ctx, const OpView& vw, const double* d_in, double* d_out, int dot_slot) {
-    return dot_slot >= 0 ? launch_fused_t<TY, TZ, ATOMIC, MINB, true>(ctx, vw, d_in, d_out, dot_slot)
-                         : launch_fused_t<TY, TZ, ATOMIC, MINB, false>(ctx, vw, d_in, d_out, -1);
+    return dot_slot >= 0 ? launch_fused_t<TY, TZ, ATOMIC, MINB, FUSE_DOT>(ctx, vw, d_in, d_out, dot_slot)
+                         : launch_fused_t<TY, TZ, ATOMIC, MINB, FUSE_PLAIN>(ctx, vw, d_in, d_out, -1);
 }
 
 bool hex8_matvec_fuses_dot(const esimp_ctx* ctx) {
@@ -546,6 +594,24 @@ int hex8_matvec_view(esimp_ctx* ctx, const OpView& vw, const double* d_in, doubl
     if (variant == ESIMP_MATVEC_FUSED_8x32) return launch_fused<8, 32, false, 2>(ctx, vw, d_in, d_out, dot_slot);
     // owner-computes tiles: 16x16 wastes less on the perimeter than 8x32
     return launch_fused<16, 16, false, 2>(ctx, vw, d_in, d_out, dot_slot);
+}
+// multigrid smoother step / residual fused into the operator's store (16x16 owner tiles only)
+int hex8_smooth_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double* z_out, const double* r, const double* dinv,
+                     double* d, double c1, double c2) {
+    ESIMP_TRY(hex8_upload_constants(ctx));
+    FuseArgs fa;
+    fa.r = r;
+    fa.dinv = dinv;
+    fa.d = d;
+    fa.c1 = c1;
+    fa.c2 = c2;
+    return launch_fused_t<16, 16, false, 2, FUSE_SMOOTH>(ctx, vw, z_in, z_out, -1, fa);
+}
+int hex8_resid_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double* res_out, const double* r) {
+    ESIMP_TRY(hex8_upload_constants(ctx));
+    FuseArgs fa;
+    fa.r = r;
+    return launch_fused_t<16, 16, false, 2, FUSE_RESID>(ctx, vw, z_in, res_out, -1, fa);
 }
 OpView fine_view(const esimp_ctx* ctx) {
     OpView v;
@@ -610,7 +676,7 @@ __global__ void k_diag_invert(GridDev g, int ps0, int ps1, const uint8_t* __rest
         int c = (int)((d / g.plane) % 3);
         long long nn = (long long)lp * g.plane + d % g.plane;
         bool fixed = (mask[nn] >> c) & 1;
-        dinv[d] = fixed ? 1.0 / m : 1.0 / dinv[d];
+        dinv[d] = fixed ? 0.0 : 1.0 / dinv[d];  // 0: prescribed dofs never move (r = 0 there; the fused smoother relies on it)
     }
 }
 

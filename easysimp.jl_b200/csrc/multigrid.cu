@@ -207,6 +207,7 @@ void mg_free(esimp_ctx* ctx) {
     for (size_t l = 0; l < ctx->mg.size(); ++l) {
         MGLevel& L = ctx->mg[l];
         cudaFree(L.d_z);
+        cudaFree(L.d_z2);
         cudaFree(L.d_d);
         cudaFree(L.d_pi);
         if (l > 0) {
@@ -248,6 +249,8 @@ static int mg_build_levels(esimp_ctx* ctx) {
         ESIMP_CUDA(cudaMalloc(&L.d_z, sizeof(double) * L.ndof_loc));
         ESIMP_CUDA(cudaMalloc(&L.d_d, sizeof(double) * L.ndof_loc));
         ESIMP_CUDA(cudaMalloc(&L.d_pi, sizeof(double) * L.ndof_loc));
+        ESIMP_CUDA(cudaMalloc(&L.d_z2, sizeof(double) * L.ndof_loc));
+        ESIMP_CUDA(cudaMemset(L.d_z2, 0, sizeof(double) * L.ndof_loc));
         ESIMP_CUDA(cudaMemset(L.d_z, 0, sizeof(double) * L.ndof_loc));
         ESIMP_CUDA(cudaMemset(L.d_d, 0, sizeof(double) * L.ndof_loc));
         ctx->mg.push_back(L);
@@ -308,7 +311,7 @@ static int mg_build_levels(esimp_ctx* ctx) {
         ESIMP_CUDA(cudaMalloc(&L.d_fixed, sizeof(long long) * std::max<long long>(L.n_fixed, 1)));
         if (L.n_fixed) ESIMP_CUDA(cudaMemcpy(L.d_fixed, fixed.data(), sizeof(long long) * L.n_fixed, cudaMemcpyHostToDevice));
         ESIMP_CUDA(cudaMalloc(&L.d_E, sizeof(double) * L.ncell_loc));
-        double** vecs[] = {&L.d_dinv, &L.d_r, &L.d_z, &L.d_d, &L.d_q, &L.d_pi};
+        double** vecs[] = {&L.d_dinv, &L.d_r, &L.d_z, &L.d_z2, &L.d_d, &L.d_q, &L.d_pi};
         for (double** v : vecs) {
             ESIMP_CUDA(cudaMalloc(v, sizeof(double) * L.ndof_loc));
             ESIMP_CUDA(cudaMemset(*v, 0, sizeof(double) * L.ndof_loc));
@@ -395,8 +398,9 @@ static int mg_smooth(esimp_ctx* ctx, MGLevel& L, int k, bool zero_guess) {
         LAUNCH_STREAM(k_cheb_first, L.d_r, L.d_dinv, 1.0 / theta, L.d_d, L.d_z, L.own_dof0, L.own_dof1);
         done = 1;
     }
+    const bool fused = ctx->prm.matvec_variant == ESIMP_MATVEC_AUTO || ctx->prm.matvec_variant == ESIMP_MATVEC_FUSED;
     for (int i = done; i < k; ++i) {
-        ESIMP_TRY(mg_apply(ctx, L, L.d_z, L.d_q));
+        if (!fused) ESIMP_TRY(mg_apply(ctx, L, L.d_z, L.d_q));
         double c1, c2;
         if (i == 0) {  // restart of the recurrence from the current iterate
             c1 = 0.0;
@@ -407,7 +411,14 @@ static int mg_smooth(esimp_ctx* ctx, MGLevel& L, int k, bool zero_guess) {
             c2 = 2.0 * rho_new / delta;
             rho = rho_new;
         }
-        LAUNCH_STREAM(k_cheb_step, L.d_r, L.d_q, L.d_dinv, c1, c2, L.d_d, L.d_z, L.own_dof0, L.own_dof1);
+        if (fused) {
+            // Chebyshev update fused into the operator's store: z' = z + c1 d + c2 Dinv (r - A z)
+            if (ctx->nranks > 1) ESIMP_TRY(comm_halo_nodes_lv(ctx, L.vw.g, L.vw.own_p0, L.vw.own_p1, L.has_left, L.has_right, L.d_z));
+            ESIMP_TRY(hex8_smooth_view(ctx, L.vw, L.d_z, L.d_z2, L.d_r, L.d_dinv, L.d_d, c1, c2));
+            std::swap(L.d_z, L.d_z2);
+        } else {
+            LAUNCH_STREAM(k_cheb_step, L.d_r, L.d_q, L.d_dinv, c1, c2, L.d_d, L.d_z, L.own_dof0, L.own_dof1);
+        }
     }
     return ESIMP_OK;
 }
@@ -418,8 +429,15 @@ static int mg_vcycle(esimp_ctx* ctx, int l) {
     if (l == (int)ctx->mg.size() - 1) return mg_smooth(ctx, L, l == 0 ? ctx->mg_nu : ctx->mg_coarse_its, true);
     MGLevel& C = ctx->mg[l + 1];
     ESIMP_TRY(mg_smooth(ctx, L, ctx->mg_nu, true));
-    ESIMP_TRY(mg_apply(ctx, L, L.d_z, L.d_q));
-    LAUNCH_STREAM(k_residual, L.d_r, L.d_q, L.own_dof0, L.own_dof1);
+    if (ctx->prm.matvec_variant == ESIMP_MATVEC_AUTO || ctx->prm.matvec_variant == ESIMP_MATVEC_FUSED) {
+        // residual fused into the operator's store: q = r - A z (prescribed rows are zeroed by the fix-up: z = 0 there)
+        if (ctx->nranks > 1) ESIMP_TRY(comm_halo_nodes_lv(ctx, L.vw.g, L.vw.own_p0, L.vw.own_p1, L.has_left, L.has_right, L.d_z));
+        ESIMP_TRY(hex8_resid_view(ctx, L.vw, L.d_z, L.d_q, L.d_r));
+        ESIMP_TRY(fixup_lv(ctx, L.d_fixed, L.n_fixed, L.diag_value, L.d_z, L.d_q));
+    } else {
+        ESIMP_TRY(mg_apply(ctx, L, L.d_z, L.d_q));
+        LAUNCH_STREAM(k_residual, L.d_r, L.d_q, L.own_dof0, L.own_dof1);
+    }
     if (ctx->nranks > 1) ESIMP_TRY(comm_halo_nodes_lv(ctx, L.vw.g, L.vw.own_p0, L.vw.own_p1, L.has_left, L.has_right, L.d_q));
     LAUNCH_STREAM(k_restrict, L.vw.g, C.vw.g, C.vw.own_p0, C.vw.own_p1, L.d_q, C.d_mask, C.d_r);
     ESIMP_TRY(mg_vcycle(ctx, l + 1));
