@@ -659,11 +659,12 @@ int esimp_profile_enable(esimp_ctx* ctx, int on) {
     ESIMP_TRY(prof_collect(ctx));
     if (on && ctx->prof_ev.empty()) {
         ctx->prof_ev.resize(2 * 4096);
+        ctx->prof_tag.assign(4096, 0);
         for (auto& e : ctx->prof_ev) ESIMP_CUDA(cudaEventCreate(&e));
     }
     ctx->prof_on = on != 0;
-    ctx->prof_ms = 0.0;
-    ctx->prof_count = 0;
+    ctx->prof_ms = ctx->prof_ms_other = 0.0;
+    ctx->prof_count = ctx->prof_count_other = 0;
     return ESIMP_OK;
 }
 int esimp_profile_matvec(esimp_ctx* ctx, double* ms_sum, int64_t* count, double* bytes_per_apply) {
@@ -674,6 +675,15 @@ int esimp_profile_matvec(esimp_ctx* ctx, double* ms_sum, int64_t* count, double*
     if (count) *count = ctx->prof_count;
     if (bytes_per_apply)
         *bytes_per_apply = 16.0 * (double)(ctx->own_dof1 - ctx->own_dof0) + 8.0 * (double)(ctx->own_cell1 - ctx->own_cell0);
+    return ESIMP_OK;
+}
+
+int esimp_profile_operator_all(esimp_ctx* ctx, double* ms_sum_all, int64_t* count_all) {
+    CHECK_CTX();
+    ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ESIMP_TRY(prof_collect(ctx));
+    if (ms_sum_all) *ms_sum_all = ctx->prof_ms + ctx->prof_ms_other;
+    if (count_all) *count_all = ctx->prof_count + ctx->prof_count_other;
     return ESIMP_OK;
 }
 

@@ -166,9 +166,10 @@ struct esimp_ctx {
     // in-region timing of the operator kernel (esimp_profile_*): event pairs recorded on ctx->stream
     bool prof_on = false;
     std::vector<cudaEvent_t> prof_ev;
+    std::vector<uint8_t> prof_tag;
     int prof_n = 0;
-    double prof_ms = 0.0;
-    int64_t prof_count = 0;
+    double prof_ms = 0.0, prof_ms_other = 0.0;
+    int64_t prof_count = 0, prof_count_other = 0;
 };
 int prof_collect(esimp_ctx* ctx);  // vector_ops.cu: fold finished event pairs into prof_ms / prof_count
 

@@ -18,7 +18,7 @@ HEADER_PATH = PKG_DIR.parent / "include" / "easysimp_b200.h"
 
 ESIMP_FILTER_SENSITIVITY, ESIMP_FILTER_DENSITY = 0, 1
 ESIMP_CELL_TET4, ESIMP_CELL_HEX8 = 4, 8
-ESIMP_MATVEC_AUTO, ESIMP_MATVEC_DENSE_ATOMIC, ESIMP_MATVEC_FUSED, ESIMP_MATVEC_FUSED_ATOMIC, ESIMP_MATVEC_FUSED_8x32 = range(5)
+ESIMP_MATVEC_AUTO, ESIMP_MATVEC_DENSE_ATOMIC, ESIMP_MATVEC_FUSED, ESIMP_MATVEC_FUSED_ATOMIC, ESIMP_MATVEC_FUSED_8x32, ESIMP_MATVEC_FUSED_8x16 = range(6)
 ESIMP_WARN_PCG_MAXIT, ESIMP_WARN_OC_MAXIT = 1, 2
 
 
@@ -87,6 +87,7 @@ _SIGNATURES = {
     "esimp_set_design": (C.c_int, [_P, _D]),
     "esimp_profile_enable": (C.c_int, [_P, C.c_int]),
     "esimp_profile_matvec": (C.c_int, [_P, _D, C.POINTER(C.c_int64), _D]),
+    "esimp_profile_operator_all": (C.c_int, [_P, _D, C.POINTER(C.c_int64)]),
 }
 
 _lib = None
@@ -321,6 +322,12 @@ class Context:
         by = C.c_double(0)
         self._chk(self.lib.esimp_profile_matvec(self._h, C.byref(ms), C.byref(n), C.byref(by)), "esimp_profile_matvec")
         return ms.value, n.value, by.value
+
+    def profile_operator_all(self):
+        ms = C.c_double(0)
+        n = C.c_int64(0)
+        self._chk(self.lib.esimp_profile_operator_all(self._h, C.byref(ms), C.byref(n)), "esimp_profile_operator_all")
+        return ms.value, n.value
 
     def bench_matvec(self, reps):
         ms = C.c_double(0)

@@ -53,6 +53,7 @@ extern "C" {
 #define ESIMP_MATVEC_FUSED 2        /* x-marching mode-space kernel, owner-computes tiles               */
 #define ESIMP_MATVEC_FUSED_ATOMIC 3 /* same, tile perimeters combined with red.global.add.f64           */
 #define ESIMP_MATVEC_FUSED_8x32 4   /* owner-computes with 8x32 (y,z) tiles instead of 16x16            */
+#define ESIMP_MATVEC_FUSED_8x16 5   /* owner-computes with 8x16 tiles, 128-thread CTAs, 4 CTAs per SM  */
 
 /* CG preconditioners */
 #define ESIMP_PRECOND_JACOBI 0 /* diagonal scaling                                                        */
@@ -188,6 +189,9 @@ int esimp_bench_matvec(esimp_ctx* ctx, int reps, double* ms_avg, double* bytes_p
  * of timed launches and the algorithmic bytes one launch moves on this rank. */
 int esimp_profile_enable(esimp_ctx* ctx, int on);
 int esimp_profile_matvec(esimp_ctx* ctx, double* ms_sum, int64_t* count, double* bytes_per_apply);
+/* same clock over EVERY fine-grid launch of the operator kernel, including the modes that fuse the multigrid smoother
+ * step / residual into the store phase (those move more bytes, so they are kept out of the roofline figure) */
+int esimp_profile_operator_all(esimp_ctx* ctx, double* ms_sum_all, int64_t* count_all);
 /* number of kernels this context has launched so far */
 int64_t esimp_launch_count(const esimp_ctx* ctx);
 

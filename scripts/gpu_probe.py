@@ -37,7 +37,7 @@ def probe(nel, variants, reps=20):
 
 
 if __name__ == "__main__":
-    V = {"fused16x16": 2, "fused_atomic8x32": 3, "fused8x32": 4}
+    V = {"fused16x16": 2, "fused_atomic8x32": 3, "fused8x32": 4, "fused8x16": 5}
     probe((240, 80, 80), dict(V, dense_atomic=1))
     t = time.time()
     probe((512, 256, 256), V, reps=10)

@@ -12,7 +12,7 @@ from oracle import simp_oracle as o
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = {"dense_atomic": 1, "fused16x16": 2, "fused_atomic8x32": 3, "fused8x32": 4}
+VARIANTS = {"dense_atomic": 1, "fused16x16": 2, "fused_atomic8x32": 3, "fused8x32": 4, "fused8x16": 5}
 
 
 def relmax(a, b):
@@ -309,7 +309,7 @@ def test_operator_properties_c4(gpu_ctx_factory, nel):
     y = 2 * o.splitmix64(idx, 2) - 1
     rho = 1e-3 + (1 - 1e-3) * o.splitmix64(np.arange(n_cells, dtype=np.uint64), 3)
     results = {}
-    for name in ("fused16x16", "fused_atomic8x32", "fused8x32"):
+    for name in ("fused16x16", "fused_atomic8x32", "fused8x32", "fused8x16"):
         ctx = gpu_ctx_factory()
         ctx.set_params(matvec_variant=VARIANTS[name])
         ctx.set_grid_structured(nx, ny, nz, 1.0, 1.0, 1.0, None)
@@ -325,6 +325,7 @@ def test_operator_properties_c4(gpu_ctx_factory, nel):
         ctx.close()
     assert relmax(results["fused_atomic8x32"], results["fused16x16"]) < 1e-12
     assert relmax(results["fused8x32"], results["fused16x16"]) < 1e-12
+    assert relmax(results["fused8x16"], results["fused16x16"]) < 1e-12
 
 
 def test_solution_properties_c4(gpu_ctx_factory):
