@@ -127,6 +127,7 @@ struct esimp_ctx {
     std::vector<MGLevel> mg;            // geometric multigrid hierarchy (precond == GMG)
     std::vector<int64_t> prescribed_nc;  // prescribed (3*node_ref + comp), kept for the coarse-level masks
     int bc_version = 0, mg_bc_version = -1;
+    int mg_min_layers = 1;  // multi-rank: stop coarsening when a rank would hold fewer cell layers than this
     int mg_nu = 2, mg_coarse_its = 16;  // tuned on 512x256x256 (scripts/mg_sweep.sh): nu 2, ratio 10 is the fastest
     double mg_ratio = 10.0;
 
@@ -197,7 +198,7 @@ OpView fine_view(const esimp_ctx* ctx);
 int hex8_matvec_view(esimp_ctx* ctx, const OpView& vw, const double* d_in, double* d_out, int variant, int dot_slot);
 int hex8_diagonal_view(esimp_ctx* ctx, const OpView& vw, double* dinv, long long n_dofs_global, double* diag_value);
 int hex8_smooth_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double* z_out, const double* r, const double* dinv,
-                     double* d, double c1, double c2);
+                     double* d, double c1, double c2, int dot_slot = -1);
 int hex8_resid_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double* res_out, const double* r);
 // multigrid.cu
 int mg_setup(esimp_ctx* ctx);          // build / refresh the hierarchy for the current E and mask

@@ -293,7 +293,7 @@ __device__ __forceinline__ void cp_async_wait() {
 //   FUSE_RESID  y = r - s                              (residual that is restricted to the next level)
 // r, Dinv, d of the plane are prefetched into registers at the start of the step (before the FP64 work), so
 // their latency is covered; the operator is FP64-bound, the extra bytes ride for free.
-enum { FUSE_PLAIN = 0, FUSE_DOT = 1, FUSE_SMOOTH = 2, FUSE_RESID = 3 };
+enum { FUSE_PLAIN = 0, FUSE_DOT = 1, FUSE_SMOOTH = 2, FUSE_RESID = 3, FUSE_SMOOTH_DOT = 4 };  // 4: FUSE_SMOOTH and <r, y>
 struct FuseArgs {
     const double* r = nullptr;
     const double* dinv = nullptr;
@@ -305,9 +305,10 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
                                                                const double* __restrict__ E, const double* __restrict__ u,
                                                                double* __restrict__ y, double* partial, unsigned int* ticket,
                                                                RedOut<1> dot_out, FuseArgs fa) {
-    constexpr bool DOT = MODE == FUSE_DOT;
+    constexpr bool DOT = MODE == FUSE_DOT || MODE == FUSE_SMOOTH_DOT;
+    constexpr bool SMOOTH = MODE == FUSE_SMOOTH || MODE == FUSE_SMOOTH_DOT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NF = MODE == FUSE_SMOOTH ? 3 : (MODE == FUSE_RESID ? 1 : 0);
+    constexpr int NF = SMOOTH ? 3 : (MODE == FUSE_RESID ? 1 : 0);
     FusedSmem<TY, TZ, NF>& sm = *reinterpret_cast<FusedSmem<TY, TZ, NF>*>(smem_raw);
     const int tid = threadIdx.x;
     const int tz = tid % TZ, ty = tid / TZ;
@@ -380,16 +381,19 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
             for (int c = 0; c < 3; ++c) {
                 double s = c00[c] + sm.out[buf][0][c][ty + 1][tz] + sm.out[buf][1][c][ty][tz + 1] + sm.out[buf][2][c][ty][tz];
                 if (own_store) {
-                    if (MODE == FUSE_SMOOTH) {
-                        const double v = fma(fa.c1, sm.fz[2 % NF][c][ty][tz], fa.c2 * sm.fz[1 % NF][c][ty][tz] * (sm.fz[0][c][ty][tz] - s));
+                    if (SMOOTH) {
+                        const double rv = sm.fz[0][c][ty][tz];
+                        const double v = fma(fa.c1, sm.fz[2 % NF][c][ty][tz], fa.c2 * sm.fz[1 % NF][c][ty][tz] * (rv - s));
                         (fa.d + foff)[c * plane] = v;
-                        py[c * plane] = sm.in[ring][c][ty][tz] + v;  // the input plane is still in its ring slot
+                        const double znew = sm.in[ring][c][ty][tz] + v;  // the input plane is still in its ring slot
+                        py[c * plane] = znew;
+                        if (MODE == FUSE_SMOOTH_DOT) pq[0] = fma(rv, znew, pq[0]);  // <r, z>: the PCG scalar of the next iteration
                     } else if (MODE == FUSE_RESID) {
                         py[c * plane] = sm.fz[0][c][ty][tz] - s;
                     } else {
                         py[c * plane] = s;
                     }
-                    if (DOT) pq[0] = fma(s, sm.in[ring][c][ty][tz], pq[0]);
+                    if (MODE == FUSE_DOT) pq[0] = fma(s, sm.in[ring][c][ty][tz], pq[0]);
                 } else if (ATOMIC && node_ok) {
                     atomicAdd(&py[c * plane], s);
                 }
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 cp_async8(&sm.fz[0][c][ty][tz], fa.r + foff + c * plane, true);
-                if (MODE == FUSE_SMOOTH) {
+                if (SMOOTH) {
                     cp_async8(&sm.fz[1 % NF][c][ty][tz], fa.dinv + foff + c * plane, true);
                     cp_async8(&sm.fz[2 % NF][c][ty][tz], fa.d + foff + c * plane, fa.c1 != 0.0);
                 }
@@ -524,7 +528,7 @@ __global__ void k_zero_perimeter(GridDev g, int ps0, int ps1, double* __restrict
 
 template <int TY, int TZ, bool ATOMIC, int MINB, int MODE>
 static int launch_fused_t(esimp_ctx* ctx, const OpView& vw, const double* d_in, double* d_out, int dot_slot, const FuseArgs& fa = FuseArgs()) {
-    constexpr bool DOT = MODE == FUSE_DOT;
+    constexpr bool DOT = MODE == FUSE_DOT || MODE == FUSE_SMOOTH_DOT;
     const GridDev& g = vw.g;
     constexpr int SY = ATOMIC ? TY : TY - 1, SZ = ATOMIC ? TZ : TZ - 1;
     const int nty = ATOMIC ? (g.ny + SY - 1) / SY : (g.ny + 1 + SY - 1) / SY;
@@ -536,7 +540,7 @@ static int launch_fused_t(esimp_ctx* ctx, const OpView& vw, const double* d_in, 
     while (chunk > 8 && tiles * ((nplanes + chunk - 1) / chunk) < 148LL * MINB * 6) chunk = (chunk + 1) / 2;
     if (ctx->fused_chunk > 0) chunk = ctx->fused_chunk;
     const int nchunk = (nplanes + chunk - 1) / chunk;
-    const size_t smem = sizeof(FusedSmem<TY, TZ, MODE == FUSE_SMOOTH ? 3 : (MODE == FUSE_RESID ? 1 : 0)>);
+    const size_t smem = sizeof(FusedSmem<TY, TZ, (MODE == FUSE_SMOOTH || MODE == FUSE_SMOOTH_DOT) ? 3 : (MODE == FUSE_RESID ? 1 : 0)>);
     static bool attr_set = false;
     auto kern = k_matvec_fused<TY, TZ, ATOMIC, MINB, MODE>;
     if (!attr_set) {
@@ -601,7 +605,7 @@ int hex8_matvec_view(esimp_ctx* ctx, const OpView& vw, const double* d_in, doubl
 }
 // multigrid smoother step / residual fused into the operator's store (16x16 owner tiles: measured faster than 8x16 for these modes)
 int hex8_smooth_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double* z_out, const double* r, const double* dinv,
-                     double* d, double c1, double c2) {
+                     double* d, double c1, double c2, int dot_slot) {
     ESIMP_TRY(hex8_upload_constants(ctx));
     FuseArgs fa;
     fa.r = r;
@@ -609,6 +613,7 @@ int hex8_smooth_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, doubl
     fa.d = d;
     fa.c1 = c1;
     fa.c2 = c2;
+    if (dot_slot >= 0) return launch_fused_t<16, 16, false, 2, FUSE_SMOOTH_DOT>(ctx, vw, z_in, z_out, dot_slot, fa);
     return launch_fused_t<16, 16, false, 2, FUSE_SMOOTH>(ctx, vw, z_in, z_out, -1, fa);
 }
 int hex8_resid_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double* res_out, const double* r) {

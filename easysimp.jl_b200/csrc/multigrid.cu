@@ -189,6 +189,24 @@ __global__ void k_mg_update(const double* __restrict__ q, double* __restrict__ r
     }
     grid_reduce<1, false>(acc, partial, ticket, out);
 }
+// same update plus the first (zero-guess) Chebyshev step of the level-0 pre-smoother on the new residual:
+// d = z = Dinv r / theta  (saves the separate k_cheb_first pass over r and Dinv)
+__global__ void k_mg_update_first(const double* __restrict__ q, double* __restrict__ r, const double* __restrict__ dinv,
+                                  double inv_theta, double* __restrict__ d, double* __restrict__ z, long long i0, long long i1,
+                                  const double* __restrict__ s_rz, const double* __restrict__ s_pq, double* partial,
+                                  unsigned int* ticket, RedOut<1> out) {
+    const double alpha = *s_rz / *s_pq;
+    double acc[1] = {0.0};
+    for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (long long)gridDim.x * blockDim.x) {
+        double ri = fma(-alpha, q[i], r[i]);
+        r[i] = ri;
+        acc[0] = fma(ri, ri, acc[0]);
+        double v = dinv[i] * ri * inv_theta;
+        d[i] = v;
+        z[i] = v;
+    }
+    grid_reduce<1, false>(acc, partial, ticket, out);
+}
 // x += alpha p;  p = z + beta p   (beta = 0 on the first call: p = z)
 __global__ void k_mg_direction(const double* __restrict__ z, double* __restrict__ p, double* __restrict__ x, long long i0, long long i1,
                                const double* __restrict__ s_rz_new, const double* __restrict__ s_rz_old,
@@ -258,7 +276,7 @@ static int mg_build_levels(esimp_ctx* ctx) {
     for (int l = 1; l < 12; ++l) {
         if ((nx & 1) || (ny & 1) || (nz & 1)) break;
         const int cx = nx / 2, cy = ny / 2, cz = nz / 2;
-        if (cx % R != 0 || cx / R < 1) break;
+        if (cx % R != 0 || cx / R < ctx->mg_min_layers) break;  // slabs: keep >= mg_min_layers cell layers per rank
         nx = cx;
         ny = cy;
         nz = cz;
@@ -389,13 +407,16 @@ int mg_setup(esimp_ctx* ctx) {
 }
 
 // k Chebyshev-Jacobi iterations on level L for A z = r
-static int mg_smooth(esimp_ctx* ctx, MGLevel& L, int k, bool zero_guess) {
+// first_done: the zero-guess first step was already applied by the caller (k_mg_update_first)
+// dot_slot >= 0: the last fused step also leaves <r, z> in d_scal[dot_slot]; *dot_done reports whether it did
+static int mg_smooth(esimp_ctx* ctx, MGLevel& L, int k, bool zero_guess, bool first_done = false, int dot_slot = -1,
+                     bool* dot_done = nullptr) {
     const double lmax = L.lmax, lmin = lmax / ctx->mg_ratio;
     const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
     double rho = 1.0 / sigma;
     int done = 0;
     if (zero_guess) {
-        LAUNCH_STREAM(k_cheb_first, L.d_r, L.d_dinv, 1.0 / theta, L.d_d, L.d_z, L.own_dof0, L.own_dof1);
+        if (!first_done) LAUNCH_STREAM(k_cheb_first, L.d_r, L.d_dinv, 1.0 / theta, L.d_d, L.d_z, L.own_dof0, L.own_dof1);
         done = 1;
     }
     const bool fused = ctx->prm.matvec_variant == ESIMP_MATVEC_AUTO || ctx->prm.matvec_variant == ESIMP_MATVEC_FUSED;
@@ -414,7 +435,9 @@ static int mg_smooth(esimp_ctx* ctx, MGLevel& L, int k, bool zero_guess) {
         if (fused) {
             // Chebyshev update fused into the operator's store: z' = z + c1 d + c2 Dinv (r - A z)
             if (ctx->nranks > 1) ESIMP_TRY(comm_halo_nodes_lv(ctx, L.vw.g, L.vw.own_p0, L.vw.own_p1, L.has_left, L.has_right, L.d_z));
-            ESIMP_TRY(hex8_smooth_view(ctx, L.vw, L.d_z, L.d_z2, L.d_r, L.d_dinv, L.d_d, c1, c2));
+            const bool with_dot = dot_slot >= 0 && i == k - 1;
+            ESIMP_TRY(hex8_smooth_view(ctx, L.vw, L.d_z, L.d_z2, L.d_r, L.d_dinv, L.d_d, c1, c2, with_dot ? dot_slot : -1));
+            if (with_dot && dot_done) *dot_done = true;
             std::swap(L.d_z, L.d_z2);
         } else {
             LAUNCH_STREAM(k_cheb_step, L.d_r, L.d_q, L.d_dinv, c1, c2, L.d_d, L.d_z, L.own_dof0, L.own_dof1);
@@ -423,12 +446,13 @@ static int mg_smooth(esimp_ctx* ctx, MGLevel& L, int k, bool zero_guess) {
     return ESIMP_OK;
 }
 
-// z_l = V(r_l)
-static int mg_vcycle(esimp_ctx* ctx, int l) {
+// z_l = V(r_l).  Level 0 only: first_done / dot_slot / dot_done as in mg_smooth.
+static int mg_vcycle(esimp_ctx* ctx, int l, bool first_done = false, int dot_slot = -1, bool* dot_done = nullptr) {
     MGLevel& L = ctx->mg[l];
-    if (l == (int)ctx->mg.size() - 1) return mg_smooth(ctx, L, l == 0 ? ctx->mg_nu : ctx->mg_coarse_its, true);
+    if (l == (int)ctx->mg.size() - 1)
+        return mg_smooth(ctx, L, l == 0 ? ctx->mg_nu : ctx->mg_coarse_its, true, first_done, dot_slot, dot_done);
     MGLevel& C = ctx->mg[l + 1];
-    ESIMP_TRY(mg_smooth(ctx, L, ctx->mg_nu, true));
+    ESIMP_TRY(mg_smooth(ctx, L, ctx->mg_nu, true, first_done));
     if (ctx->prm.matvec_variant == ESIMP_MATVEC_AUTO || ctx->prm.matvec_variant == ESIMP_MATVEC_FUSED) {
         // residual fused into the operator's store: q = r - A z (prescribed rows are zeroed by the fix-up: z = 0 there)
         if (ctx->nranks > 1) ESIMP_TRY(comm_halo_nodes_lv(ctx, L.vw.g, L.vw.own_p0, L.vw.own_p1, L.has_left, L.has_right, L.d_z));
@@ -449,7 +473,7 @@ static int mg_vcycle(esimp_ctx* ctx, int l) {
         ctx->launches++;
         ESIMP_CUDA(cudaGetLastError());
     }
-    return mg_smooth(ctx, L, ctx->mg_nu, false);
+    return mg_smooth(ctx, L, ctx->mg_nu, false, false, dot_slot, dot_done);
 }
 
 __global__ void k_dot2(const double* __restrict__ a, const double* __restrict__ b, long long i0, long long i1, double* partial,
@@ -502,8 +526,11 @@ int pcg_solve_mg(esimp_ctx* ctx, int* iters, double* relres) {
             ESIMP_TRY(vec_dot(ctx, ctx->d_p, ctx->d_q, SC_PQ));
         }
         {
+            // r -= alpha q, <r,r>, and the first Chebyshev step of the coming V-cycle (d = z = Dinv r / theta)
+            const double lmax0 = L0.lmax, theta0 = 0.5 * (lmax0 + lmax0 / ctx->mg_ratio);
             RedOut<1> out{{S + SC_RR0}};
-            LAUNCH_STREAM(k_mg_update, ctx->d_q, ctx->d_r, i0, i1, S + RZ[cur], S + SC_PQ, ctx->d_partial, ctx->d_ticket, out);
+            LAUNCH_STREAM(k_mg_update_first, ctx->d_q, ctx->d_r, L0.d_dinv, 1.0 / theta0, L0.d_d, L0.d_z, i0, i1, S + RZ[cur], S + SC_PQ,
+                          ctx->d_partial, ctx->d_ticket, out);
             ESIMP_TRY(allreduce_scalars(ctx, SC_RR0, 1, false));
         }
         ++it;
@@ -516,12 +543,13 @@ int pcg_solve_mg(esimp_ctx* ctx, int* iters, double* relres) {
             LAUNCH_STREAM(k_mg_direction, L0.d_z, ctx->d_p, ctx->d_u, i0, i1, S + RZ[cur], S + RZ[cur], S + SC_PQ, 2);
             break;
         }
-        ESIMP_TRY(mg_vcycle(ctx, 0));
-        {
+        bool dot_done = false;
+        ESIMP_TRY(mg_vcycle(ctx, 0, true, RZ[nxt], &dot_done));  // <r,z> comes out of the last fused smoother step
+        if (!dot_done) {
             RedOut<1> out{{S + RZ[nxt]}};
             LAUNCH_STREAM(k_dot2, ctx->d_r, L0.d_z, i0, i1, ctx->d_partial, ctx->d_ticket, out);
-            ESIMP_TRY(allreduce_scalars(ctx, RZ[nxt], 1, false));
         }
+        ESIMP_TRY(allreduce_scalars(ctx, RZ[nxt], 1, false));
         LAUNCH_STREAM(k_mg_direction, L0.d_z, ctx->d_p, ctx->d_u, i0, i1, S + RZ[nxt], S + RZ[cur], S + SC_PQ, 0);
     }
     if (rr > tol2) status = ESIMP_WARN_PCG_MAXIT;
