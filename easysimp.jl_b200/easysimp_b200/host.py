@@ -343,6 +343,7 @@ class OptimizationParameters:
     pcg_maxit: int = 200000
     pcg_check_every: int = 25
     matvec_variant: int = 0
+    preconditioner: str = "auto"  # "jacobi" | "gmg" | "auto" (gmg on generate_grid grids, jacobi on imported meshes)
 
 
 @dataclass
@@ -368,7 +369,8 @@ def _configure(ctx, grid, params: OptimizationParameters, fcache: FilterCache):
     ctx.set_params(E0=params.E0, Emin=params.Emin, nu=params.nu, p=params.p, volume_fraction=params.volume_fraction,
                    move_limit=params.move_limit, damping=params.damping, filter_radius=fcache.filter_radius, filter_type=ftype,
                    pcg_rtol=params.pcg_rtol, pcg_maxit=params.pcg_maxit, pcg_check_every=params.pcg_check_every,
-                   matvec_variant=params.matvec_variant, warm_start=1)
+                   matvec_variant=params.matvec_variant, warm_start=1,
+                   precond=int(params.preconditioner == "gmg" or (params.preconditioner == "auto" and fcache.structured)))
     if fcache.structured:
         ctx.filter_build_structured()
     else:

@@ -95,10 +95,11 @@ end
 
 "Mesh + BCs + load + filter into a context.  Everything density independent is uploaded once."
 function configure!(ctx::Context, grid, dh, loads, boundary_conditions, params::OptimizationParameters, fc::FilterCache)
-    prm = EsimpParams(params.E0, params.Emin, params.ν, params.p, params.volume_fraction, params.move_limit, params.damping,
-                      fc.filter_radius, params.filter_type == :density ? 1 : 0, 200000, 1e-8, 25, 0, 1, 0)
-    check(ctx, ccall((:esimp_set_params, LIB), Cint, (Ptr{Cvoid}, Ref{EsimpParams}), ctx.ptr, prm), "esimp_set_params")
     sd = structured_dims(grid)
+    # last field: CG preconditioner, ESIMP_PRECOND_GMG (1) on generate_grid grids, ESIMP_PRECOND_JACOBI (0) on imported meshes
+    prm = EsimpParams(params.E0, params.Emin, params.ν, params.p, params.volume_fraction, params.move_limit, params.damping,
+                      fc.filter_radius, params.filter_type == :density ? 1 : 0, 200000, 1e-8, 25, 0, 1, sd !== nothing ? 1 : 0)
+    check(ctx, ccall((:esimp_set_params, LIB), Cint, (Ptr{Cvoid}, Ref{EsimpParams}), ctx.ptr, prm), "esimp_set_params")
     if sd !== nothing
         don = dof_of_node(dh)
         check(ctx, ccall((:esimp_set_grid_structured, LIB), Cint,
