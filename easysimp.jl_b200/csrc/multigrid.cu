@@ -88,26 +88,39 @@ __global__ void k_restrict(GridDev gf, GridDev gc, int cp0, int cp1, const doubl
 }
 
 // z_f += P z_c on the owned fine nodes (trilinear interpolation), prescribed fine dofs untouched.
-// Branch-free: along each axis the two parents are index>>1 and (index+1)>>1 (the same node for an even index),
-// each with weight 1/2.  blockIdx.y walks (plane, component), threads walk the (y,z) plane.
+// One thread per coarse (J,K) position of a (plane, component): it loads its 2x2 coarse parents (x 1 or 2 coarse
+// planes) once and updates the 2x2 patch of fine nodes (2J+a, 2K+b) -- 4-8 loads for 4 outputs instead of 8 each.
+// Along each axis the parents of fine index i are i>>1 and (i+1)>>1 with weight 1/2 each (the same node if i is even).
 __global__ void __launch_bounds__(256) k_prolong_add(GridDev gf, GridDev gc, int fp0, int fp1, const double* __restrict__ zc,
                                                      const uint8_t* __restrict__ maskf, double* __restrict__ zf) {
-    const int nyz = (gf.ny + 1) * (gf.nz + 1), nzf = gf.nz + 1;
+    const int nJ = gc.ny + 1, nK = gc.nz + 1, nJK = nJ * nK, nzf = gf.nz + 1;
     for (int pc = blockIdx.y; pc < (fp1 - fp0) * 3; pc += gridDim.y) {
         const int lp = fp0 + pc / 3, c = pc % 3;
         const int Gf = gf.gp0 + lp;
-        const int lpc0 = (Gf >> 1) - gc.gp0, lpc1 = ((Gf + 1) >> 1) - gc.gp0;
-        const double* __restrict__ c0 = zc + (long long)(lpc0 * 3 + c) * gc.plane;
-        const double* __restrict__ c1 = zc + (long long)(lpc1 * 3 + c) * gc.plane;
+        const bool two = Gf & 1;  // odd fine plane: average of two coarse planes
+        const double* __restrict__ c0 = zc + (long long)(((Gf >> 1) - gc.gp0) * 3 + c) * gc.plane;
+        const double* __restrict__ c1 = zc + (long long)((((Gf + 1) >> 1) - gc.gp0) * 3 + c) * gc.plane;
         double* __restrict__ zrow = zf + (long long)(lp * 3 + c) * gf.plane;
         const uint8_t* __restrict__ mrow = maskf + (long long)lp * gf.plane;
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nyz; i += gridDim.x * blockDim.x) {
-            const int j = i / nzf, k = i - j * nzf;
-            if ((mrow[i] >> c) & 1) continue;
-            const int J0 = (j >> 1) * (gc.nz + 1), J1 = ((j + 1) >> 1) * (gc.nz + 1), K0 = k >> 1, K1 = (k + 1) >> 1;
-            const double s = (c0[J0 + K0] + c0[J0 + K1]) + (c0[J1 + K0] + c0[J1 + K1]) + (c1[J0 + K0] + c1[J0 + K1]) +
-                             (c1[J1 + K0] + c1[J1 + K1]);
-            zrow[i] = fma(0.125, s, zrow[i]);
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nJK; i += gridDim.x * blockDim.x) {
+            const int J = i / nK, K = i - J * nK;
+            const bool hasJ = J < gc.ny, hasK = K < gc.nz;  // the last coarse row / column only owns the even fine index
+            const int o00 = J * nK + K, o01 = o00 + (hasK ? 1 : 0), o10 = o00 + (hasJ ? nK : 0), o11 = o10 + (hasK ? 1 : 0);
+            double v00 = c0[o00], v01 = c0[o01], v10 = c0[o10], v11 = c0[o11];
+            if (two) {
+                v00 = 0.5 * (v00 + c1[o00]);
+                v01 = 0.5 * (v01 + c1[o01]);
+                v10 = 0.5 * (v10 + c1[o10]);
+                v11 = 0.5 * (v11 + c1[o11]);
+            }
+            const int f00 = (2 * J) * nzf + 2 * K;
+            if (!((mrow[f00] >> c) & 1)) zrow[f00] += v00;
+            if (hasK && !((mrow[f00 + 1] >> c) & 1)) zrow[f00 + 1] += 0.5 * (v00 + v01);
+            if (hasJ) {
+                const int f10 = f00 + nzf;
+                if (!((mrow[f10] >> c) & 1)) zrow[f10] += 0.5 * (v00 + v10);
+                if (hasK && !((mrow[f10 + 1] >> c) & 1)) zrow[f10 + 1] += 0.25 * ((v00 + v01) + (v10 + v11));
+            }
         }
     }
 }
@@ -467,7 +480,7 @@ static int mg_vcycle(esimp_ctx* ctx, int l, bool first_done = false, int dot_slo
     ESIMP_TRY(mg_vcycle(ctx, l + 1));
     if (ctx->nranks > 1) ESIMP_TRY(comm_halo_nodes_lv(ctx, C.vw.g, C.vw.own_p0, C.vw.own_p1, C.has_left, C.has_right, C.d_z));
     {
-        const int nyz = (L.vw.g.ny + 1) * (L.vw.g.nz + 1);
+        const int nyz = (C.vw.g.ny + 1) * (C.vw.g.nz + 1);  // one thread per coarse (J,K) position
         dim3 grid((unsigned)std::min(64, (nyz + 255) / 256), (unsigned)std::min(65535, (L.vw.own_p1 - L.vw.own_p0) * 3));
         k_prolong_add<<<grid, 256, 0, ctx->stream>>>(L.vw.g, C.vw.g, L.vw.own_p0, L.vw.own_p1, C.d_z, L.d_mask, L.d_z);
         ctx->launches++;

@@ -36,3 +36,24 @@ def slab_partition(nx: int, rank: int, nranks: int, halo_e: int = 1) -> Slab:
     npx = (ex1 - ex0) + 1 + left
     return Slab(rank, nranks, ex0, ex1, ex0 - left, npx, left, npx - right, ex0 - gl, (ex1 - ex0) + gl + gr, gl,
                 gl + (ex1 - ex0), gl - left, gl + (ex1 - ex0), he)
+
+
+def multigrid_levels(nel, nranks: int, min_layers: int = 1, max_levels: int = 12):
+    """Grid hierarchy csrc/multigrid.cu builds (mg_build_levels): halve every dimension while all three are even and
+    every rank keeps >= min_layers whole cell layers (coarse nx divisible by nranks).  Returns [(nx, ny, nz), ...]."""
+    nx, ny, nz = nel
+    levels = [(nx, ny, nz)]
+    while len(levels) < max_levels:
+        if nx % 2 or ny % 2 or nz % 2:
+            break
+        cx = nx // 2
+        if cx % nranks or cx // nranks < min_layers:
+            break
+        nx, ny, nz = cx, ny // 2, nz // 2
+        levels.append((nx, ny, nz))
+    return levels
+
+
+def level_slab(level_nx: int, rank: int, nranks: int) -> Slab:
+    """Slab of one multigrid level (one ghost cell layer per interior side on coarse levels)."""
+    return slab_partition(level_nx, rank, nranks, 1)

@@ -119,3 +119,39 @@ def test_slab_partition_covers_grid():
             assert s.ge0 + s.mv_e0 == s.gp0 and s.ge0 + s.mv_e1 == s.gp0 + s.npx - 1
             assert s.nex == (s.ex1 - s.ex0) + s.halo_e * ((s.rank > 0) + (s.rank < R - 1))
         assert owned_planes == list(range(nx + 1))
+
+
+def test_multigrid_slab_hierarchy_invariants():
+    """What the slab-aware V-cycle (csrc/multigrid.cu) relies on: on every level each node plane is owned by exactly
+    one rank; coarse plane I and fine plane 2I are owned by the SAME rank (restriction / prolongation are local up to
+    the one-plane halo); the fine planes 2I-1, 2I+1 a restriction reads and the coarse planes (i-1)/2, (i+1)/2 a
+    prolongation reads are stored (owned or ghost) on that rank."""
+    from easysimp_b200.partition import level_slab, multigrid_levels
+
+    assert multigrid_levels((512, 256, 256), 1) == [(512 >> l, 256 >> l, 256 >> l) for l in range(9)]
+    assert multigrid_levels((512, 256, 256), 8)[-1] == (8, 4, 4) and len(multigrid_levels((512, 256, 256), 8)) == 7
+    assert multigrid_levels((60, 20, 4), 1) == [(60, 20, 4), (30, 10, 2), (15, 5, 1)]
+    assert multigrid_levels((60, 20, 4), 4) == [(60, 20, 4)]  # 30 layers do not split over 4 ranks
+    for nel, R in [((512, 256, 256), 8), ((512, 256, 256), 2), ((64, 16, 16), 2), ((40, 20, 20), 2), ((96, 8, 8), 3)]:
+        levels = multigrid_levels(nel, R)
+        for lf, lc in zip(levels[:-1], levels[1:]):
+            owner_f, owner_c = {}, {}
+            stored_f, stored_c = {}, {}
+            for r in range(R):
+                sf, sc = level_slab(lf[0], r, R), level_slab(lc[0], r, R)
+                for p in range(sf.gp0 + sf.own_p0, sf.gp0 + sf.own_p1):
+                    assert p not in owner_f
+                    owner_f[p] = r
+                for p in range(sc.gp0 + sc.own_p0, sc.gp0 + sc.own_p1):
+                    assert p not in owner_c
+                    owner_c[p] = r
+                stored_f[r] = set(range(sf.gp0, sf.gp0 + sf.npx))
+                stored_c[r] = set(range(sc.gp0, sc.gp0 + sc.npx))
+            assert sorted(owner_f) == list(range(lf[0] + 1)) and sorted(owner_c) == list(range(lc[0] + 1))
+            for I, r in owner_c.items():
+                assert owner_f[2 * I] == r
+                for p in (2 * I - 1, 2 * I + 1):
+                    assert p < 0 or p > lf[0] or p in stored_f[r]
+            for i, r in owner_f.items():
+                for P in ({i // 2} if i % 2 == 0 else {(i - 1) // 2, (i + 1) // 2}):
+                    assert P in stored_c[r]
