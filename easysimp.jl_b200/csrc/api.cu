@@ -116,6 +116,8 @@ int esimp_create(esimp_ctx** out, int device) {
     if (const char* e = getenv("ESIMP_MG_COARSE_ITS")) ctx->mg_coarse_its = std::max(1, atoi(e));
     if (const char* e = getenv("ESIMP_MG_RATIO")) ctx->mg_ratio = std::max(1.5, atof(e));
     if (const char* e = getenv("ESIMP_MG_MIN_LAYERS")) ctx->mg_min_layers = std::max(1, atoi(e));
+    if (const char* e = getenv("ESIMP_MG_REPLICATE")) ctx->mg_replicate = atoi(e);
+    if (const char* e = getenv("ESIMP_MG_REPLICATE_CELLS")) ctx->mg_replicate_cells = atoll(e);
     auto bail = [&](const char* what) {
         std::string msg = std::string(what) + ": " + cudaGetErrorString(cudaGetLastError());
         delete ctx;

@@ -76,6 +76,7 @@ struct MGLevel {
     double* d_pi = nullptr;  // power-iteration vector, kept between SIMP iterations (warm start of the lmax estimate)
     bool pi_valid = false;
     bool owns = false;
+    bool replicated = false;  // multi-rank: every rank holds the whole (small) grid of this level, no communication
 };
 
 struct UnstructuredMesh {
@@ -127,6 +128,8 @@ struct esimp_ctx {
     std::vector<MGLevel> mg;            // geometric multigrid hierarchy (precond == GMG)
     std::vector<int64_t> prescribed_nc;  // prescribed (3*node_ref + comp), kept for the coarse-level masks
     int bc_version = 0, mg_bc_version = -1;
+    int mg_replicate = 1;                   // multi-rank: replicate the deep levels instead of stopping / exchanging halos
+    long long mg_replicate_cells = 100000;  // levels with at most this many cells (global) are replicated (64x32x32 at C5)
     int mg_min_layers = 1;  // multi-rank: stop coarsening when a rank would hold fewer cell layers than this
     int mg_nu = 2, mg_coarse_its = 16;  // tuned on 512x256x256 (scripts/mg_sweep.sh): nu 2, ratio 10 is the fastest
     double mg_ratio = 10.0;

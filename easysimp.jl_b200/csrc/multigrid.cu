@@ -286,16 +286,32 @@ static int mg_build_levels(esimp_ctx* ctx) {
         ESIMP_CUDA(cudaMemset(L.d_d, 0, sizeof(double) * L.ndof_loc));
         ctx->mg.push_back(L);
     }
-    for (int l = 1; l < 12; ++l) {
+    bool replicated = false;
+    for (int l = 1; l < 14; ++l) {
         if ((nx & 1) || (ny & 1) || (nz & 1)) break;
         const int cx = nx / 2, cy = ny / 2, cz = nz / 2;
-        if (cx % R != 0 || cx / R < ctx->mg_min_layers) break;  // slabs: keep >= mg_min_layers cell layers per rank
+        // Slabs: a level stays distributed while every rank keeps >= mg_min_layers whole cell layers and the level is
+        // big enough to be worth its halo exchanges; below that the level (and every coarser one) is REPLICATED: each
+        // rank holds the whole small grid, the restricted residual is summed with one allreduce, and nothing under
+        // that level communicates (the deep levels of a slab hierarchy are pure NCCL latency otherwise).
+        if (R > 1 && !replicated) {
+            const bool can_split = cx % R == 0 && cx / R >= ctx->mg_min_layers;
+            if (!can_split || (long long)cx * cy * cz <= ctx->mg_replicate_cells) {
+                if (!ctx->mg_replicate) {
+                    if (!can_split) break;
+                } else {
+                    replicated = true;
+                }
+            }
+        }
         nx = cx;
         ny = cy;
         nz = cz;
-        const int ex0 = (int)((long long)nx * r / R), ex1 = (int)((long long)nx * (r + 1) / R);
-        const int left = ctx->has_left ? 1 : 0, right = ctx->has_right ? 1 : 0;
+        const bool rp = replicated;
+        const int ex0 = rp ? 0 : (int)((long long)nx * r / R), ex1 = rp ? nx : (int)((long long)nx * (r + 1) / R);
+        const int left = (!rp && ctx->has_left) ? 1 : 0, right = (!rp && ctx->has_right) ? 1 : 0;
         MGLevel L;
+        L.replicated = rp;
         GridDev& g = L.vw.g;
         g.nx = nx;
         g.ny = ny;
@@ -311,8 +327,8 @@ static int mg_build_levels(esimp_ctx* ctx) {
         L.vw.own_p1 = g.NPX - right;
         L.vw.mv_e0 = 0;  // owned layers + the redundant left interface layer
         L.vw.mv_e1 = left + (ex1 - ex0);
-        L.has_left = ctx->has_left;
-        L.has_right = ctx->has_right;
+        L.has_left = left != 0;
+        L.has_right = right != 0;
         L.ndof_loc = 3LL * g.NPX * g.plane;
         L.ncell_loc = (long long)g.NEX * g.eplane;
         L.own_dof0 = 3LL * L.vw.own_p0 * g.plane;
@@ -353,6 +369,17 @@ static int mg_build_levels(esimp_ctx* ctx) {
     }
     return ESIMP_OK;
 }
+
+// While a replicated level is processed the context behaves like a single-rank one: every halo exchange and
+// allreduce is skipped (all ranks execute the same deterministic kernels on the same data).
+struct LocalScope {
+    esimp_ctx* c;
+    int saved;
+    LocalScope(esimp_ctx* ctx, bool on) : c(ctx), saved(ctx->nranks) {
+        if (on) c->nranks = 1;
+    }
+    ~LocalScope() { c->nranks = saved; }
+};
 
 static int mg_apply(esimp_ctx* ctx, MGLevel& L, double* in, double* out, int dot_slot = -1) {
     if (ctx->nranks > 1) ESIMP_TRY(comm_halo_nodes_lv(ctx, L.vw.g, L.vw.own_p0, L.vw.own_p1, L.has_left, L.has_right, in));
@@ -401,19 +428,33 @@ int mg_setup(esimp_ctx* ctx) {
     ctx->mg[0].diag_value = ctx->diag_value;
     for (size_t l = 1; l < ctx->mg.size(); ++l) {
         MGLevel &F = ctx->mg[l - 1], &C = ctx->mg[l];
-        const int left = C.has_left ? 1 : 0;
-        LAUNCH_STREAM(k_restrict_E, F.vw.g, C.vw.g, left, left + (int)((C.own_cell1 - C.own_cell0) / C.vw.g.eplane), F.d_E, C.d_E);
-        if (ctx->nranks > 1)
-            ESIMP_TRY(comm_halo_cells_lv(ctx, C.vw.g, left, left + (int)((C.own_cell1 - C.own_cell0) / C.vw.g.eplane), 1, C.has_left,
-                                         C.has_right, C.d_E));
+        if (C.replicated && !F.replicated) {
+            // distributed -> replicated: a rank restricts the coarse layers I whose first child layer 2I it owns (the
+            // second child may be its right ghost layer), the rest of the full-grid array is summed in by an allreduce
+            const int fe0 = F.vw.g.ge0 + (int)(F.own_cell0 / F.vw.g.eplane), fe1 = F.vw.g.ge0 + (int)(F.own_cell1 / F.vw.g.eplane);
+            ESIMP_CUDA(cudaMemsetAsync(C.d_E, 0, sizeof(double) * C.ncell_loc, ctx->stream));
+            LAUNCH_STREAM(k_restrict_E, F.vw.g, C.vw.g, (fe0 + 1) / 2, (fe1 + 1) / 2, F.d_E, C.d_E);
+            ESIMP_TRY(comm_allreduce(ctx, C.d_E, (int)C.ncell_loc, false));
+        } else {
+            LocalScope ls(ctx, C.replicated);
+            const int left = C.has_left ? 1 : 0;
+            LAUNCH_STREAM(k_restrict_E, F.vw.g, C.vw.g, left, left + (int)((C.own_cell1 - C.own_cell0) / C.vw.g.eplane), F.d_E, C.d_E);
+            if (ctx->nranks > 1)
+                ESIMP_TRY(comm_halo_cells_lv(ctx, C.vw.g, left, left + (int)((C.own_cell1 - C.own_cell0) / C.vw.g.eplane), 1,
+                                             C.has_left, C.has_right, C.d_E));
+        }
+        LocalScope ls(ctx, C.replicated);
         ESIMP_TRY(hex8_diagonal_view(ctx, C.vw, C.d_dinv, C.n_dofs_global, &C.diag_value));
     }
-    for (auto& L : ctx->mg) ESIMP_TRY(mg_estimate_lmax(ctx, L, 8));
+    for (auto& L : ctx->mg) {
+        LocalScope ls(ctx, L.replicated);
+        ESIMP_TRY(mg_estimate_lmax(ctx, L, 8));
+    }
     if (getenv("ESIMP_MG_DEBUG"))
         for (size_t l = 0; l < ctx->mg.size(); ++l) {
             const MGLevel& L = ctx->mg[l];
-            fprintf(stderr, "[mg rank %d] level %zu: %dx%dx%d NPX %d NEX %d own_p [%d,%d) mv_e [%d,%d) n_fixed %lld diag_value %.6e lmax %.4f\n", ctx->rank,
-                    l, L.vw.g.nx, L.vw.g.ny, L.vw.g.nz, L.vw.g.NPX, L.vw.g.NEX, L.vw.own_p0, L.vw.own_p1, L.vw.mv_e0, L.vw.mv_e1, L.n_fixed,
+            fprintf(stderr, "[mg rank %d] level %zu%s: %dx%dx%d NPX %d NEX %d own_p [%d,%d) mv_e [%d,%d) n_fixed %lld diag_value %.6e lmax %.4f\n", ctx->rank,
+                    l, L.replicated ? " (replicated)" : "", L.vw.g.nx, L.vw.g.ny, L.vw.g.nz, L.vw.g.NPX, L.vw.g.NEX, L.vw.own_p0, L.vw.own_p1, L.vw.mv_e0, L.vw.mv_e1, L.n_fixed,
                     L.diag_value, L.lmax);
         }
     return ESIMP_OK;
@@ -476,9 +517,21 @@ static int mg_vcycle(esimp_ctx* ctx, int l, bool first_done = false, int dot_slo
         LAUNCH_STREAM(k_residual, L.d_r, L.d_q, L.own_dof0, L.own_dof1);
     }
     if (ctx->nranks > 1) ESIMP_TRY(comm_halo_nodes_lv(ctx, L.vw.g, L.vw.own_p0, L.vw.own_p1, L.has_left, L.has_right, L.d_q));
-    LAUNCH_STREAM(k_restrict, L.vw.g, C.vw.g, C.vw.own_p0, C.vw.own_p1, L.d_q, C.d_mask, C.d_r);
-    ESIMP_TRY(mg_vcycle(ctx, l + 1));
-    if (ctx->nranks > 1) ESIMP_TRY(comm_halo_nodes_lv(ctx, C.vw.g, C.vw.own_p0, C.vw.own_p1, C.has_left, C.has_right, C.d_z));
+    if (C.replicated && !L.replicated) {
+        // distributed -> replicated: restrict onto the coarse planes I whose fine plane 2I this rank owns (their
+        // neighbours 2I-1, 2I+1 are owned or ghost planes), sum the full coarse vector over the ranks, then run the
+        // rest of the cycle without any communication; the prolongation back reads the local full coarse grid
+        const int fp0g = L.vw.g.gp0 + L.vw.own_p0, fp1g = L.vw.g.gp0 + L.vw.own_p1;  // owned fine planes, global
+        ESIMP_CUDA(cudaMemsetAsync(C.d_r, 0, sizeof(double) * C.ndof_loc, ctx->stream));
+        LAUNCH_STREAM(k_restrict, L.vw.g, C.vw.g, (fp0g + 1) / 2, (fp1g - 1) / 2 + 1, L.d_q, C.d_mask, C.d_r);
+        ESIMP_TRY(comm_allreduce(ctx, C.d_r, (int)C.ndof_loc, false));
+        LocalScope ls(ctx, true);
+        ESIMP_TRY(mg_vcycle(ctx, l + 1));
+    } else {
+        LAUNCH_STREAM(k_restrict, L.vw.g, C.vw.g, C.vw.own_p0, C.vw.own_p1, L.d_q, C.d_mask, C.d_r);
+        ESIMP_TRY(mg_vcycle(ctx, l + 1));
+        if (ctx->nranks > 1) ESIMP_TRY(comm_halo_nodes_lv(ctx, C.vw.g, C.vw.own_p0, C.vw.own_p1, C.has_left, C.has_right, C.d_z));
+    }
     {
         const int nyz = (C.vw.g.ny + 1) * (C.vw.g.nz + 1);  // one thread per coarse (J,K) position
         dim3 grid((unsigned)std::min(64, (nyz + 255) / 256), (unsigned)std::min(65535, (L.vw.own_p1 - L.vw.own_p0) * 3));
