@@ -142,6 +142,8 @@ int esimp_destroy(esimp_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     comm_destroy(ctx);
     free_mesh_state(ctx);
+    hex8_forget_ctx(ctx);
+    filter_forget_ctx(ctx);
     cudaFree(ctx->d_partial);
     cudaFree(ctx->d_partial_mv);
     cudaFree(ctx->d_ticket);

@@ -99,7 +99,7 @@ void comm_destroy(esimp_ctx* ctx) {
     ctx->nccl_comm = nullptr;
 }
 
-int comm_allreduce(esimp_ctx* ctx, double* d_buf, int n, bool is_max) {
+int comm_allreduce(esimp_ctx* ctx, double* d_buf, long long n, bool is_max) {
     if (ctx->nranks <= 1) return ESIMP_OK;
     ESIMP_NCCL(g_nccl.AllReduce(d_buf, d_buf, (size_t)n, ncclDouble, is_max ? ncclMax : ncclSum, (ncclComm_t)ctx->nccl_comm,
                                 ctx->stream));

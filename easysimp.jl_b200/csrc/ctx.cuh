@@ -195,6 +195,8 @@ enum {
 // ------------------------------------------------------------------ module entry points
 // hex8_structured.cu
 int hex8_upload_constants(esimp_ctx* ctx);
+void hex8_forget_ctx(const esimp_ctx* ctx);
+void filter_forget_ctx(const esimp_ctx* ctx);
 int hex8_matvec(esimp_ctx* ctx, const double* d_in, double* d_out, int variant, int dot_slot = -1);
 bool hex8_matvec_fuses_dot(const esimp_ctx* ctx);
 OpView fine_view(const esimp_ctx* ctx);
@@ -247,7 +249,7 @@ void tet4_element_matrix(const double* xyz4, double lam, double mu, double* ke12
 int comm_unique_id(void* id128, std::string& err);
 int comm_init(esimp_ctx* ctx, int rank, int nranks, const void* id128);
 void comm_destroy(esimp_ctx* ctx);
-int comm_allreduce(esimp_ctx* ctx, double* d_buf, int n, bool is_max);
+int comm_allreduce(esimp_ctx* ctx, double* d_buf, long long n, bool is_max);
 int comm_halo_nodes(esimp_ctx* ctx, double* d_vec);            // one-plane u halo, both directions
 int comm_halo_cells(esimp_ctx* ctx, double* d_arr);            // halo_e-layer cell halo, both directions
 

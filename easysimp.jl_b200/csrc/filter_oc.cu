@@ -42,6 +42,9 @@ int simp_modulus(esimp_ctx* ctx) {
 }
 
 // ---------------------------------------------------------------------------- stencil filter
+void filter_forget_ctx(const esimp_ctx* ctx) {
+    if (g_stencil_owner == ctx) g_stencil_owner = nullptr;
+}
 static int upload_stencil(esimp_ctx* ctx) {
     if (g_stencil_owner == ctx) return ESIMP_OK;
     std::vector<int> di(ctx->st_n), dj(ctx->st_n), dk(ctx->st_n);

@@ -119,6 +119,11 @@ void tet4_element_matrix(const double* xyz, double lam, double mu, double* ke) {
     add_gradients(4, g, lam, mu, fabs(det) / 6.0, ke);
 }
 
+// a destroyed context must not be mistaken for the owner of the constants by a later one at the same address
+void hex8_forget_ctx(const esimp_ctx* ctx) {
+    if (g_const_owner == ctx) g_const_owner = nullptr;
+}
+
 // Build K0 (unit modulus), its mode-space blocks and the nodal diagonal for the context's cuboid.
 int hex8_upload_constants(esimp_ctx* ctx) {
     if (!ctx->k0_valid) {

@@ -434,7 +434,7 @@ int mg_setup(esimp_ctx* ctx) {
             const int fe0 = F.vw.g.ge0 + (int)(F.own_cell0 / F.vw.g.eplane), fe1 = F.vw.g.ge0 + (int)(F.own_cell1 / F.vw.g.eplane);
             ESIMP_CUDA(cudaMemsetAsync(C.d_E, 0, sizeof(double) * C.ncell_loc, ctx->stream));
             LAUNCH_STREAM(k_restrict_E, F.vw.g, C.vw.g, (fe0 + 1) / 2, (fe1 + 1) / 2, F.d_E, C.d_E);
-            ESIMP_TRY(comm_allreduce(ctx, C.d_E, (int)C.ncell_loc, false));
+            ESIMP_TRY(comm_allreduce(ctx, C.d_E, C.ncell_loc, false));
         } else {
             LocalScope ls(ctx, C.replicated);
             const int left = C.has_left ? 1 : 0;
@@ -524,7 +524,7 @@ static int mg_vcycle(esimp_ctx* ctx, int l, bool first_done = false, int dot_slo
         const int fp0g = L.vw.g.gp0 + L.vw.own_p0, fp1g = L.vw.g.gp0 + L.vw.own_p1;  // owned fine planes, global
         ESIMP_CUDA(cudaMemsetAsync(C.d_r, 0, sizeof(double) * C.ndof_loc, ctx->stream));
         LAUNCH_STREAM(k_restrict, L.vw.g, C.vw.g, (fp0g + 1) / 2, (fp1g - 1) / 2 + 1, L.d_q, C.d_mask, C.d_r);
-        ESIMP_TRY(comm_allreduce(ctx, C.d_r, (int)C.ndof_loc, false));
+        ESIMP_TRY(comm_allreduce(ctx, C.d_r, C.ndof_loc, false));
         LocalScope ls(ctx, true);
         ESIMP_TRY(mg_vcycle(ctx, l + 1));
     } else {
