@@ -44,7 +44,7 @@ static int ensure_stage(esimp_ctx* ctx, int64_t n) {
 static void free_mesh_state(esimp_ctx* ctx) {
     void* ptrs[] = {ctx->d_dof_of_node, ctx->d_filtD, ctx->d_mask, ctx->d_fixed, ctx->d_f, ctx->d_u, ctx->d_r, ctx->d_p,
                     ctx->d_q, ctx->d_dinv, ctx->d_rho, ctx->d_phys, ctx->d_E, ctx->d_dc, ctx->d_dcf, ctx->d_dv,
-                    ctx->d_rho_new, ctx->d_rho_old, ctx->d_ctmp, ctx->d_stage};
+                    ctx->d_rho_new, ctx->d_rho_old, ctx->d_ctmp, ctx->d_stage, ctx->d_fload};
     for (void* p : ptrs) cudaFree(p);
     ctx->d_dof_of_node = nullptr;
     ctx->d_filtD = nullptr;
@@ -53,6 +53,9 @@ static void free_mesh_state(esimp_ctx* ctx) {
     ctx->d_f = ctx->d_u = ctx->d_r = ctx->d_p = ctx->d_q = ctx->d_dinv = nullptr;
     ctx->d_rho = ctx->d_phys = ctx->d_E = ctx->d_dc = ctx->d_dcf = ctx->d_dv = ctx->d_rho_new = ctx->d_rho_old = ctx->d_ctmp = nullptr;
     ctx->d_stage = nullptr;
+    ctx->d_fload = nullptr;
+    ctx->body_on = false;
+    post_forget_ctx(ctx);
     ctx->stage_cap = 0;
     ctx->n_fixed = 0;
     um_free(ctx);
@@ -347,9 +350,49 @@ int esimp_set_load(esimp_ctx* ctx, const double* f) {
     NEED(ctx->structured || ctx->unstructured, "no mesh");
     if (!f) return esimp_fail(ctx, ESIMP_ERR_ARG, "f is NULL");
     ESIMP_TRY(upload_dofs(ctx, f, ctx->d_f));
+    if (ctx->body_on) {  // f is rebuilt from this density-independent part on every assembly
+        ESIMP_CUDA(cudaMemcpyAsync(ctx->d_fload, ctx->d_f, sizeof(double) * ctx->ndof_loc, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->density_set = false;
+    }
     ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->load_set = true;
     return ESIMP_OK;
+}
+
+int esimp_set_body_force(esimp_ctx* ctx, const double* accel3, double base_density) {
+    CHECK_CTX();
+    NEED(ctx->structured || ctx->unstructured, "no mesh");
+    const size_t bytes = sizeof(double) * ctx->ndof_loc;
+    if (!accel3) {  // off: f goes back to the density-independent loads
+        if (ctx->body_on) ESIMP_CUDA(cudaMemcpyAsync(ctx->d_f, ctx->d_fload, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->body_on = false;
+        ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));
+        return ESIMP_OK;
+    }
+    if (!ctx->body_on) {
+        if (!ctx->d_fload) ESIMP_TRY(dev_alloc(ctx, &ctx->d_fload, ctx->ndof_loc));
+        if (ctx->load_set)
+            ESIMP_CUDA(cudaMemcpyAsync(ctx->d_fload, ctx->d_f, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        else
+            ESIMP_CUDA(cudaMemsetAsync(ctx->d_fload, 0, bytes, ctx->stream));
+    }
+    for (int c = 0; c < 3; ++c) ctx->body_b[c] = accel3[c];
+    ctx->body_base = base_density;
+    ctx->body_on = true;
+    ctx->load_set = true;      // a body force alone is a valid right-hand side
+    ctx->density_set = false;  // f now depends on the density: esimp_set_density / esimp_iterate rebuild it
+    ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ESIMP_OK;
+}
+
+int esimp_body_force(esimp_ctx* ctx, const double* accel3, const double* density_data, double* f_body) {
+    CHECK_CTX();
+    NEED(ctx->structured || ctx->unstructured, "no mesh");
+    if (!accel3 || !density_data || !f_body) return esimp_fail(ctx, ESIMP_ERR_ARG, "NULL argument");
+    // stage call: borrows d_ctmp / d_q as scratch
+    ESIMP_TRY(upload_cells(ctx, density_data, ctx->d_ctmp));
+    ESIMP_TRY(body_force_into(ctx, ctx->d_ctmp, 1.0, accel3, nullptr, ctx->d_q));
+    return download_dofs(ctx, ctx->d_q, f_body);
 }
 
 int esimp_filter_build_structured(esimp_ctx* ctx) {
@@ -374,6 +417,7 @@ static int prepare_operator(esimp_ctx* ctx) {
     else
         ESIMP_TRY(um_diagonal(ctx));
     if (ctx->prm.precond == ESIMP_PRECOND_GMG && ctx->structured) ESIMP_TRY(mg_setup(ctx));
+    ESIMP_TRY(body_force_refresh_rhs(ctx));  // Optimization.jl:300-311
     ctx->density_set = true;
     return ESIMP_OK;
 }
@@ -620,6 +664,36 @@ int esimp_final_analysis(esimp_ctx* ctx, double* energy, double* volume, int* pc
     ESIMP_TRY(fetch_scalars(ctx));
     if (energy) *energy = ctx->h_scal[SC_ENERGY];  // :534
     if (volume) *volume = ctx->h_scal[SC_VOL];     // :535
+    return st;
+}
+
+int esimp_stress_nq(const esimp_ctx* ctx) { return !ctx ? 0 : ctx->structured ? 8 : ctx->unstructured ? (ctx->um.npe == 8 ? 8 : 1) : 0; }
+
+int esimp_stress_fields(esimp_ctx* ctx, double* von_mises_q1, double* von_mises_avg, double* element_energy, double* max_von_mises,
+                        int64_t* max_cell) {
+    CHECK_CTX();
+    NEED(ctx->density_set, "esimp_set_density / esimp_iterate first");
+    ESIMP_TRY(stress_fields(ctx, max_von_mises, max_cell));
+    if (von_mises_q1) ESIMP_TRY(download_cells(ctx, ctx->d_ctmp, von_mises_q1));
+    if (von_mises_avg) ESIMP_TRY(download_cells(ctx, ctx->d_dcf, von_mises_avg));
+    if (element_energy) ESIMP_TRY(download_cells(ctx, ctx->d_rho_new, element_energy));
+    return ESIMP_OK;
+}
+
+int esimp_stress_tensors(esimp_ctx* ctx, int64_t cell0, int64_t n, double* sigma) {
+    CHECK_CTX();
+    NEED(ctx->density_set, "esimp_set_density / esimp_iterate first");
+    if (!sigma) return esimp_fail(ctx, ESIMP_ERR_ARG, "NULL array");
+    if (cell0 < 0 || n < 0 || cell0 + n > ctx->n_cells_global) return esimp_fail(ctx, ESIMP_ERR_ARG, "cell range outside the mesh");
+    if (n == 0) return ESIMP_OK;
+    const int64_t len = n * esimp_stress_nq(ctx) * 6;
+    double* d_out = nullptr;
+    ESIMP_CUDA(cudaMalloc(&d_out, sizeof(double) * len));
+    int st = stress_tensors(ctx, cell0, n, d_out);
+    if (st >= 0 && cudaMemcpyAsync(sigma, d_out, sizeof(double) * len, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+        st = esimp_fail(ctx, ESIMP_ERR_CUDA, "stress tensor download failed");
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(d_out);
     return st;
 }
 

@@ -94,6 +94,9 @@ struct UnstructuredMesh {
     int32_t* d_col = nullptr;
     double* d_w = nullptr;           // max(0, R - dist)
     double* d_D = nullptr;           // D_i = sum_j w_ij V_j
+    // body force / stress recovery (post_load.cu), colour-sorted and entry-major like d_ke
+    double* d_nint = nullptr;        // [npe][n_cells] int N_a dOmega (2x2x2 Gauss on hexes, V/4 on tets)
+    double* d_xcell = nullptr;       // [3*npe][n_cells] node coordinates of each cell
 };
 
 struct NcclApi;  // comm.cu
@@ -165,6 +168,10 @@ struct esimp_ctx {
     double* d_scal = nullptr;       // device scalars (see SC_* in vector_ops.cu)
     double* h_scal = nullptr;       // pinned mirror
     bool density_set = false, load_set = false, design_set = false;
+    // variable-density body force (Optimization.jl:300-311): f = fload + body(rho_phys * body_base) on every assembly
+    bool body_on = false;
+    double body_b[3] = {0.0, 0.0, 0.0}, body_base = 0.0;
+    double* d_fload = nullptr;  // density-independent part of f (allocated when the body force is switched on)
     double f_norm2 = 0.0;
     cudaEvent_t ev[6]{};
     // in-region timing of the operator kernel (esimp_profile_*): event pairs recorded on ctx->stream
@@ -197,6 +204,12 @@ enum {
 int hex8_upload_constants(esimp_ctx* ctx);
 void hex8_forget_ctx(const esimp_ctx* ctx);
 void filter_forget_ctx(const esimp_ctx* ctx);
+void post_forget_ctx(const esimp_ctx* ctx);
+// post_load.cu
+int body_force_into(esimp_ctx* ctx, const double* d_dens, double base, const double b[3], const double* d_fload, double* d_out);
+int body_force_refresh_rhs(esimp_ctx* ctx);  // d_f = d_fload + body(d_phys) when the body force is on
+int stress_fields(esimp_ctx* ctx, double* max_vm, int64_t* max_cell);  // d_ctmp = vm(q1), d_dcf = vm(avg), d_rho_new = energy
+int stress_tensors(esimp_ctx* ctx, int64_t id0, int64_t n, double* d_out);
 int hex8_matvec(esimp_ctx* ctx, const double* d_in, double* d_out, int variant, int dot_slot = -1);
 bool hex8_matvec_fuses_dot(const esimp_ctx* ctx);
 OpView fine_view(const esimp_ctx* ctx);

@@ -93,7 +93,31 @@ void um_free(esimp_ctx* ctx) {
     cudaFree(um.d_col);
     cudaFree(um.d_w);
     cudaFree(um.d_D);
+    cudaFree(um.d_nint);
+    cudaFree(um.d_xcell);
     um = UnstructuredMesh();
+}
+
+// int N_a dOmega with the 2x2x2 rule of the cell values (the fe_body weights of FiniteElementAnalysis.jl:503-514)
+static void hex_shape_integrals(const double* x, double* out8) {
+    static const double HEXREF[8][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1},
+                                        {-1, -1, 1},  {1, -1, 1},  {1, 1, 1},  {-1, 1, 1}};
+    const double gp = 1.0 / sqrt(3.0);
+    for (int a = 0; a < 8; ++a) out8[a] = 0.0;
+    for (int q = 0; q < 8; ++q) {
+        const double xi[3] = {(q & 1) ? gp : -gp, (q & 2) ? gp : -gp, (q & 4) ? gp : -gp};
+        double J[3][3] = {{0}}, N[8];
+        for (int a = 0; a < 8; ++a) {
+            double f0 = 1 + HEXREF[a][0] * xi[0], f1 = 1 + HEXREF[a][1] * xi[1], f2 = 1 + HEXREF[a][2] * xi[2];
+            double dN[3] = {0.125 * HEXREF[a][0] * f1 * f2, 0.125 * f0 * HEXREF[a][1] * f2, 0.125 * f0 * f1 * HEXREF[a][2]};
+            N[a] = 0.125 * f0 * f1 * f2;
+            for (int c = 0; c < 3; ++c)
+                for (int d = 0; d < 3; ++d) J[c][d] += x[3 * a + c] * dN[d];
+        }
+        double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                     J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+        for (int a = 0; a < 8; ++a) out8[a] += N[a] * fabs(det);
+    }
 }
 
 static double hex_volume(const double* x) {
@@ -173,7 +197,7 @@ int um_build(esimp_ctx* ctx, int celltype, int64_t n_cells, int64_t n_nodes, con
     const double nu = ctx->prm.nu;
     const double lam = nu / ((1 + nu) * (1 - 2 * nu)), mu = 1.0 / (2 * (1 + nu));
     std::vector<int32_t> cd((size_t)nd * n_cells);
-    std::vector<double> ke((size_t)nd * nd * n_cells), vol(n_cells);
+    std::vector<double> ke((size_t)nd * nd * n_cells), vol(n_cells), nint((size_t)npe * n_cells), xcell((size_t)nd * n_cells);
     std::vector<double> kel(nd * nd), x(3 * npe);
     for (int64_t s = 0; s < n_cells; ++s) {
         int64_t e = order[s];
@@ -185,8 +209,12 @@ int um_build(esimp_ctx* ctx, int celltype, int64_t n_cells, int64_t n_nodes, con
             tet4_element_matrix(x.data(), lam, mu, kel.data());
         for (int l = 0; l < nd; ++l) cd[(size_t)l * n_cells + s] = (int32_t)celldofs[e * nd + l];
         for (int q = 0; q < nd * nd; ++q) ke[(size_t)q * n_cells + s] = kel[q];
+        for (int l = 0; l < nd; ++l) xcell[(size_t)l * n_cells + s] = x[l];
         if (npe == 8) {
             vol[e] = hex_volume(x.data());
+            double ni[8];
+            hex_shape_integrals(x.data(), ni);
+            for (int a = 0; a < 8; ++a) nint[(size_t)a * n_cells + s] = ni[a];
         } else {
             double J[3][3];
             for (int c = 0; c < 3; ++c)
@@ -194,6 +222,7 @@ int um_build(esimp_ctx* ctx, int celltype, int64_t n_cells, int64_t n_nodes, con
             double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
                          J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
             vol[e] = fabs(det) / 6.0;
+            for (int a = 0; a < 4; ++a) nint[(size_t)a * n_cells + s] = vol[e] / 4.0;  // linear N_a: exact with the order-2 rule
         }
     }
     ESIMP_CUDA(cudaMalloc(&um.d_order, sizeof(int32_t) * n_cells));
@@ -204,6 +233,10 @@ int um_build(esimp_ctx* ctx, int celltype, int64_t n_cells, int64_t n_nodes, con
     ESIMP_CUDA(cudaMemcpy(um.d_celldofs, cd.data(), sizeof(int32_t) * cd.size(), cudaMemcpyHostToDevice));
     ESIMP_CUDA(cudaMemcpy(um.d_ke, ke.data(), sizeof(double) * ke.size(), cudaMemcpyHostToDevice));
     ESIMP_CUDA(cudaMemcpy(um.d_vol, vol.data(), sizeof(double) * n_cells, cudaMemcpyHostToDevice));
+    ESIMP_CUDA(cudaMalloc(&um.d_nint, sizeof(double) * nint.size()));
+    ESIMP_CUDA(cudaMalloc(&um.d_xcell, sizeof(double) * xcell.size()));
+    ESIMP_CUDA(cudaMemcpy(um.d_nint, nint.data(), sizeof(double) * nint.size(), cudaMemcpyHostToDevice));
+    ESIMP_CUDA(cudaMemcpy(um.d_xcell, xcell.data(), sizeof(double) * xcell.size(), cudaMemcpyHostToDevice));
     return ESIMP_OK;
 }
 

@@ -131,7 +131,9 @@ def setup_problem(grid: Grid, interpolation_order: int = 1, device: int = -1, ct
         npe = grid.cells.shape[1]
         ctx.set_mesh_unstructured(npe, grid.coords, grid.cells, dh.celldofs())
     K = StiffnessOperator(ctx, dh)
-    cellvalues = {"celltype": Hexahedron if grid.cells.shape[1] == 8 else Tetrahedron, "quadrature_order": 2}
+    # the quadrature lives in the kernels; the placeholder carries the context so that the functions the reference
+    # calls with (dh, cellvalues) and no K -- body force, stress recovery -- find the device state
+    cellvalues = {"celltype": Hexahedron if grid.cells.shape[1] == 8 else Tetrahedron, "quadrature_order": 2, "ctx": ctx}
     return dh, cellvalues, K, np.zeros(dh.ndofs)
 
 
@@ -206,6 +208,62 @@ def apply_force_(f, dh, nodes, force_vector):
         if d[0] >= 0:
             f[d] += per
     return f
+
+
+def apply_variable_density_volume_force_(f, dh, cellvalues, body_force_vector, density_data):
+    """apply_variable_density_volume_force! (FEA.jl:486-526): f += sum_e density_e * b * int N dOmega, cells with
+    density < 1e-6 skipped.  Inside simp_optimize the library does this on the device at every assembly
+    (`acceleration_data`); this is the stand-alone form."""
+    fb = cellvalues["ctx"].body_force(body_force_vector, density_data)
+    f += fb
+    return f
+
+
+class StressField:
+    """What `stress_field::Dict{Int,Vector{SymmetricTensor}}` (FEA.jl:566-597) becomes: three cell arrays computed on
+    the device plus on-demand Gauss-point tensors.  `field[cell]` -> (nq, 6) in SymmetricTensor storage order
+    (11 21 31 22 32 33), valid while the context still holds the state the field was computed from."""
+
+    def __init__(self, ctx, fields):
+        self._ctx = ctx
+        self.von_mises_q1 = fields["vm_q1"]  # calculate_von_mises_stresses, PostProcessing.jl:204-222
+        self.von_mises_avg = fields["vm_avg"]  # FEA.jl:584
+        self.element_energy = fields["element_energy"]  # calculate_element_energy, PostProcessing.jl:172-198
+        self.max_von_mises = fields["max_vm"]
+        self.max_cell = fields["max_cell"]
+
+    def __len__(self):
+        return 0 if self.von_mises_q1 is None else self.von_mises_q1.size
+
+    def __getitem__(self, cell):
+        return self._ctx.stress_tensors(int(cell), 1)[0]
+
+    def tensors(self, cell0=0, n=None):
+        return self._ctx.stress_tensors(cell0, n)
+
+
+def calculate_stresses_simp(u, dh, cellvalues, material_model, density_data):
+    """calculate_stresses_simp (FEA.jl:566-597) -> (stress_field, max_von_mises, max_vm_cell_id); cell ids are 0-based
+    here (-1 = none).  Uploads u and the densities; simp_optimize calls the device-resident form instead."""
+    ctx = cellvalues["ctx"]
+    ctx.set_params(E0=material_model.E0, Emin=material_model.Emin, nu=material_model.nu, p=material_model.p)
+    ctx.set_density(np.asarray(density_data, dtype=np.float64))
+    ctx.set_displacement(np.asarray(u, dtype=np.float64))
+    sf = StressField(ctx, ctx.stress_fields())
+    return sf, sf.max_von_mises, sf.max_cell
+
+
+def create_results_data(grid, dh, cellvalues, opt_result):
+    """create_results_data + the cell/point arrays export_main_results writes (PostProcessing.jl:39-110).  The
+    `displacement` array is indexed by node through the dof handler (the reference's extract_nodal_displacements,
+    :147-165, assumes dof = 3(node-1)+c, which Ferrite's numbering does not guarantee)."""
+    u = opt_result.displacements
+    nodal = np.where(dh.dof_of_node >= 0, u[np.maximum(dh.dof_of_node, 0)], 0.0).T  # (3, n_nodes)
+    st = opt_result.stresses
+    return dict(density=opt_result.densities, von_mises_stress=st.von_mises_q1, element_energy=st.element_energy,
+                displacement=nodal, displacement_magnitude=np.linalg.norm(nodal, axis=0), energy=opt_result.energy,
+                volume_fraction=opt_result.volume / float(np.sum(calculate_element_volumes(grid))),
+                iterations=opt_result.iterations, converged=opt_result.converged)
 
 
 @dataclass
@@ -348,12 +406,12 @@ class OptimizationParameters:
 
 @dataclass
 class OptimizationResult:
-    """OptimizationResult (Optimization.jl:145-155); `stresses` stays empty: stress recovery
-    (FEA.jl:537-597) is off the per-iteration path and remains the host's job."""
+    """OptimizationResult (Optimization.jl:145-155); `stresses` is a StressField (device-computed von Mises /
+    element-energy arrays + on-demand Gauss-point tensors) instead of a Dict of tensors."""
 
     densities: np.ndarray
     displacements: np.ndarray
-    stresses: dict
+    stresses: object
     energy: float
     volume: float
     iterations: int
@@ -381,8 +439,6 @@ def simp_optimize(grid, dh, cellvalues, loads, boundary_conditions, params: Opti
                   K: StiffnessOperator | None = None, on_iteration=None) -> OptimizationResult:
     """simp_optimize (Optimization.jl:178-565).  The loop control is here; the loop BODY (:273-379)
     is one `esimp_iterate` call whose state never leaves the device."""
-    if acceleration_data is not None:
-        raise NotImplementedError("variable-density body force (FEA.jl:486-526) is outside the hot-path scope (SURVEY 8f-4)")
     if K is None:
         raise ValueError("pass the operator handle returned by setup_problem as K=")
     ctx = K.ctx
@@ -398,6 +454,10 @@ def simp_optimize(grid, dh, cellvalues, loads, boundary_conditions, params: Opti
     _configure(ctx, grid, params, fcache)
     ctx.set_dirichlet(prescribed)
     ctx.set_load(f)
+    if acceleration_data is not None:  # (acceleration_vector, base_density), :195-198, applied on every assembly :300-311
+        ctx.set_body_force(acceleration_data[0], acceleration_data[1])
+    else:
+        ctx.set_body_force(None)
     ctx.init_design(None)  # fill(volume_fraction), :222
     energy_history, volume_history, stats = [], [], []
     triggered = [False] * len(params.tolerance_checkpoints)
@@ -414,10 +474,13 @@ def simp_optimize(grid, dh, cellvalues, loads, boundary_conditions, params: Opti
         for idx, cp in enumerate(params.tolerance_checkpoints):  # :407-445 (export stays with the caller)
             if not triggered[idx] and s.change < cp:
                 triggered[idx] = True
-                checkpoints[cp] = dict(iteration=iteration, densities=ctx.get_physical_density(), energy=s.energy)
+                # :417-424: stresses of the checkpoint state, computed where u lives
+                checkpoints[cp] = dict(iteration=iteration, densities=ctx.get_physical_density(), energy=s.energy,
+                                       stresses=StressField(ctx, ctx.stress_fields()))
         if s.change < params.tolerance:  # :484-488
             converged = True
             break
     energy, volume, _ = ctx.final_analysis()  # :494-535
-    return OptimizationResult(ctx.get_physical_density(), ctx.get_displacement(), {}, energy, volume, iteration, converged,
+    stresses = StressField(ctx, ctx.stress_fields())  # :537-539
+    return OptimizationResult(ctx.get_physical_density(), ctx.get_displacement(), stresses, energy, volume, iteration, converged,
                               energy_history, volume_history, stats, checkpoints)

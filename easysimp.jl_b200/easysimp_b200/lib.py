@@ -88,6 +88,11 @@ _SIGNATURES = {
     "esimp_profile_enable": (C.c_int, [_P, C.c_int]),
     "esimp_profile_matvec": (C.c_int, [_P, _D, C.POINTER(C.c_int64), _D]),
     "esimp_profile_operator_all": (C.c_int, [_P, _D, C.POINTER(C.c_int64)]),
+    "esimp_set_body_force": (C.c_int, [_P, _D, C.c_double]),
+    "esimp_body_force": (C.c_int, [_P, _D, _D, _D]),
+    "esimp_stress_fields": (C.c_int, [_P, _D, _D, _D, _D, _I64]),
+    "esimp_stress_tensors": (C.c_int, [_P, C.c_int64, C.c_int64, _D]),
+    "esimp_stress_nq": (C.c_int, [_P]),
 }
 
 _lib = None
@@ -181,6 +186,43 @@ class Context:
         k, p = _f64(f)
         assert k.size == self.n_dofs
         self._chk(self.lib.esimp_set_load(self._h, p), "esimp_set_load")
+
+    def set_body_force(self, accel=None, base_density=0.0):
+        """acceleration_data of simp_optimize (Optimization.jl:300-311); accel=None switches it off."""
+        if accel is None:
+            self._chk(self.lib.esimp_set_body_force(self._h, None, 0.0), "esimp_set_body_force")
+            return
+        k, p = _f64(np.asarray(accel, dtype=np.float64).reshape(3))
+        self._chk(self.lib.esimp_set_body_force(self._h, p, float(base_density)), "esimp_set_body_force")
+
+    def body_force(self, accel, density_data):
+        a, pa = _f64(np.asarray(accel, dtype=np.float64).reshape(3))
+        d, pd = _f64(density_data)
+        assert d.size == self.n_cells
+        out = np.empty(self.n_dofs)
+        self._chk(self.lib.esimp_body_force(self._h, pa, pd, out.ctypes.data_as(_D)), "esimp_body_force")
+        return out
+
+    def stress_fields(self, want_fields=True):
+        """-> dict(vm_q1, vm_avg, element_energy, max_vm, max_cell); the arrays are None with want_fields=False."""
+        n = self.n_cells
+        arrs = [np.empty(n) for _ in range(3)] if want_fields else [None] * 3
+        ptrs = [a.ctypes.data_as(_D) if a is not None else None for a in arrs]
+        mx = C.c_double(0)
+        cell = C.c_int64(-1)
+        self._chk(self.lib.esimp_stress_fields(self._h, ptrs[0], ptrs[1], ptrs[2], C.byref(mx), C.byref(cell)), "esimp_stress_fields")
+        return dict(vm_q1=arrs[0], vm_avg=arrs[1], element_energy=arrs[2], max_vm=mx.value, max_cell=cell.value)
+
+    @property
+    def stress_nq(self):
+        return int(self.lib.esimp_stress_nq(self._h))
+
+    def stress_tensors(self, cell0=0, n=None):
+        """sigma[n, nq, 6] of the caller's cells [cell0, cell0+n) (SymmetricTensor storage order 11 21 31 22 32 33)."""
+        n = self.n_cells - cell0 if n is None else n
+        out = np.empty((n, self.stress_nq, 6))
+        self._chk(self.lib.esimp_stress_tensors(self._h, cell0, n, out.ctypes.data_as(_D)), "esimp_stress_tensors")
+        return out
 
     def filter_build_structured(self):
         self._chk(self.lib.esimp_filter_build_structured(self._h), "esimp_filter_build_structured")

@@ -133,6 +133,13 @@ int esimp_set_params(esimp_ctx* ctx, const esimp_params* p);
 int esimp_set_dirichlet(esimp_ctx* ctx, const int64_t* dofs, int64_t n);
 /* assembled load vector (apply_load_condition!, LoadConditions.jl:112-154), length n_dofs */
 int esimp_set_load(esimp_ctx* ctx, const double* f);
+/* variable-density body force = simp_optimize's `acceleration_data = (acceleration_vector, base_density)`:
+ * on EVERY assembly f = load + sum_e rho_phys_e * base_density * b * int N dOmega, cells whose density is below 1e-6
+ * skipped (apply_variable_density_volume_force!, FiniteElementAnalysis.jl:486-526, called at Optimization.jl:300-311
+ * and :517-528).  accel3 = NULL switches it off.  A body force alone is a valid right-hand side. */
+int esimp_set_body_force(esimp_ctx* ctx, const double* accel3, double base_density);
+/* stage call: f_body (length n_dofs, caller numbering) for density_data[n_cells] = rho_phys .* base_density */
+int esimp_body_force(esimp_ctx* ctx, const double* accel3, const double* density_data, double* f_body);
 
 /* ---- filter (FilterCache, FilterCommon.jl:40-98) ---------------------------------------- */
 /* structured: stencil from R = params.filter_radius; uniform element volume */
@@ -169,6 +176,23 @@ int esimp_init_design(esimp_ctx* ctx, const double* rho);
 int esimp_iterate(esimp_ctx* ctx, esimp_iter_stats* out);
 /* final analysis (Optimization.jl:494-535): re-filter, re-solve, energy, volume */
 int esimp_final_analysis(esimp_ctx* ctx, double* energy, double* volume, int* pcg_iters);
+
+/* ---- post-solve fields for the export branches (Optimization.jl:407-477, :537-539) ----- */
+/* For the displacement and physical densities on the device (after esimp_iterate / esimp_final_analysis / esimp_solve):
+ *   von_mises_q1[n_cells]   von Mises stress of the FIRST Gauss point of each cell = the exported "von_mises_stress"
+ *                           field (calculate_von_mises_stresses, PostProcessing.jl:204-222)
+ *   von_mises_avg[n_cells]  von Mises stress of the Gauss-point average, whose maximum and first cell attaining it are
+ *                           what calculate_stresses_simp returns (FiniteElementAnalysis.jl:566-597); max_cell is
+ *                           0-based, -1 when every value is 0
+ *   element_energy[n_cells] 1/2 sum_q sigma:eps dOmega (calculate_element_energy, PostProcessing.jl:172-198)
+ * Lame parameters per cell from E(rho_phys) like material_model(density) (:577).  Any output pointer may be NULL. */
+int esimp_stress_fields(esimp_ctx* ctx, double* von_mises_q1, double* von_mises_avg, double* element_energy,
+                        double* max_von_mises, int64_t* max_cell);
+/* the `stress_field` Dict itself, for the caller's cells [cell0, cell0+n): sigma[n][nq][6], nq = esimp_stress_nq
+ * (8 Gauss points on hexahedra, first coordinate fastest; 1 on linear tetrahedra whose 4 points carry the same tensor),
+ * 6 = SymmetricTensor{2,3} storage order (11, 21, 31, 22, 32, 33).  Chunk the range to bound host memory. */
+int esimp_stress_tensors(esimp_ctx* ctx, int64_t cell0, int64_t n, double* sigma);
+int esimp_stress_nq(const esimp_ctx* ctx);
 
 /* ---- state I/O ------------------------------------------------------------------------- */
 int esimp_get_design(esimp_ctx* ctx, double* rho);           /* design variables           */

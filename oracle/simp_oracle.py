@@ -444,10 +444,12 @@ class IterationRecord:
 
 
 def simp_optimize(grid, dof_of_node, f_load, prescribed, params: OptimizationParameters,
-                  solver="direct", pcg_rtol=1e-12, keep_fields=False):
+                  solver="direct", pcg_rtol=1e-12, keep_fields=False, acceleration_data=None):
     """Restatement of the loop at Optimization.jl:271-489 plus the final analysis :494-535.
     `f_load` is the assembled load vector (apply_load_condition! output, density independent),
-    `prescribed` the union of all ConstraintHandler prescribed dofs.  Returns a dict."""
+    `prescribed` the union of all ConstraintHandler prescribed dofs; `acceleration_data` =
+    (acceleration_vector, base_density) adds the variable-density body force to f before the
+    loads and constraints on every assembly (:300-311, :517-528).  Returns a dict."""
     n_c = grid.n_cells
     V = element_volumes(grid)
     Vtot = float(V.sum())
@@ -466,7 +468,10 @@ def simp_optimize(grid, dof_of_node, f_load, prescribed, params: OptimizationPar
     def solve_state(rho_phys, u0):
         E = simp_modulus(rho_phys, params.E0, params.Emin, params.p)
         K = assemble_stiffness(grid, dof_of_node, E / params.E0, k_unit)
-        Kbc, fbc, _ = apply_dirichlet(K, f_load.copy(), prescribed)
+        f = f_load.copy()
+        if acceleration_data is not None:
+            f += body_force(grid, dof_of_node, acceleration_data[0], rho_phys * acceleration_data[1])
+        Kbc, fbc, _ = apply_dirichlet(K, f, prescribed)
         if solver == "direct":
             uu = solve_direct(Kbc, fbc)
         else:
@@ -495,6 +500,107 @@ def simp_optimize(grid, dof_of_node, f_load, prescribed, params: OptimizationPar
     u, energy = solve_state(phys, u)
     return dict(densities=phys, design=rho, displacements=u, energy=energy, volume=float(phys @ V),
                 iterations=it, converged=converged, history=hist, fields=fields)
+
+
+# --------------------------------------------------------------------------------------
+# Body force, stress recovery and the export fields (the density-dependent load inside the
+# loop, Optimization.jl:300-311; the post-solve fields of Optimization.jl:407-477, :537-539)
+# --------------------------------------------------------------------------------------
+
+_GP = 1.0 / math.sqrt(3.0)
+# QuadratureRule{RefHexahedron}(2): tensor product, first coordinate fastest; point 1 = (-g,-g,-g)
+_HEX_QP = np.array([[sx, sy, sz] for sz in (-_GP, _GP) for sy in (-_GP, _GP) for sx in (-_GP, _GP)])
+_TET_DN = np.array([[-1.0, -1.0, -1.0], [1.0, 0.0, 0.0], [0.0, 1.0, 0.0], [0.0, 0.0, 1.0]])
+
+
+def _hex_N(xi):
+    s = _HEX_REF
+    f = 1.0 + s * xi[None, :]
+    return 0.125 * f[:, 0] * f[:, 1] * f[:, 2]
+
+
+def body_force(grid, dof_of_node, accel, density_data) -> np.ndarray:
+    """apply_variable_density_volume_force! (FiniteElementAnalysis.jl:486-526) on a zero f:
+    fe[(a,c)] = sum_q density * b_c * N_a(q) * dOmega_q, cells with density < 1e-6 skipped
+    (:495-497), added into f in cell order (:519-521)."""
+    cd = celldofs(grid, dof_of_node)
+    f = np.zeros(int(dof_of_node.max()) + 1)
+    accel = np.asarray(accel, dtype=np.float64)
+    for e in range(grid.n_cells):
+        dens = density_data[e]
+        if dens < 1e-6:
+            continue
+        X = grid.coords[grid.cells[e]]
+        fe = np.zeros(3 * grid.npe)
+        if grid.npe == 8:
+            for xi in _HEX_QP:
+                dN = _hex_dN(xi)
+                dvol = abs(np.linalg.det(X.T @ dN))  # weight 1
+                N = _hex_N(xi)
+                fe += (dens * accel[None, :] * N[:, None] * dvol).ravel()  # fe[3a+c] += density * b_c * N_a * dOmega (:505-512)
+        else:
+            # order-2 rule on the tetrahedron integrates the linear N_a exactly: int N_a = V / 4
+            vol = abs(np.linalg.det(X.T @ _TET_DN)) / 6.0
+            fe += np.tile(dens * accel * vol / 4.0, 4)
+        np.add.at(f, cd[e], fe)
+    return f
+
+
+def stress_voigt(eps, lam, mu):
+    """constitutive_relation (FiniteElementAnalysis.jl:63-65) on a symmetric 3x3 strain."""
+    return lam * np.trace(eps) * np.eye(3) + 2.0 * mu * eps
+
+
+def von_mises(sig):
+    """sqrt(3/2 dev(s):dev(s)) (FiniteElementAnalysis.jl:584, PostProcessing.jl:216-217)."""
+    dev = sig - np.trace(sig) / 3.0 * np.eye(3)
+    return math.sqrt(1.5 * float(np.sum(dev * dev)))
+
+
+# SymmetricTensor{2,3} storage order (lower triangle, column major): 11 21 31 22 32 33
+_SYM_IJ = [(0, 0), (1, 0), (2, 0), (1, 1), (2, 1), (2, 2)]
+
+
+def stresses_simp(grid, dof_of_node, u, E0, nu, Emin, p, density_data):
+    """calculate_stresses_simp (FiniteElementAnalysis.jl:566-597) + the two consumers of its
+    output in PostProcessing.jl: calculate_von_mises_stresses (:204-222, uses the FIRST
+    quadrature point of each cell) and calculate_element_energy (:172-198).
+    Returns dict(sigma [n_c, n_q, 6], vm_avg, max_vm, max_cell (0-based, -1 if none),
+    vm_q1, element_energy)."""
+    cd = celldofs(grid, dof_of_node)
+    nq = 8 if grid.npe == 8 else 1
+    sigma = np.zeros((grid.n_cells, nq, 6))
+    vm_avg = np.zeros(grid.n_cells)
+    vm_q1 = np.zeros(grid.n_cells)
+    energy = np.zeros(grid.n_cells)
+    max_vm, max_cell = 0.0, -1
+    for e in range(grid.n_cells):
+        lam, mu = lame(float(simp_modulus(density_data[e], E0, Emin, p)), nu)  # material_model(density), :577
+        X = grid.coords[grid.cells[e]]
+        ue = u[cd[e]].reshape(grid.npe, 3)
+        avg = np.zeros((3, 3))
+        W = 0.0
+        if grid.npe == 8:
+            qps = [(_hex_dN(xi), 1.0) for xi in _HEX_QP]
+        else:
+            qps = [(_TET_DN, 1.0 / 6.0)]  # constant gradient: the 4 points of the rule coincide in value
+        for q, (dN, w) in enumerate(qps):
+            J = X.T @ dN
+            g = dN @ np.linalg.inv(J)
+            grad_u = ue.T @ g  # grad_u[c, d] = d u_c / d x_d   (function_gradient, :543)
+            eps = 0.5 * (grad_u + grad_u.T)
+            sig = stress_voigt(eps, lam, mu)
+            sigma[e, q] = [sig[i, j] for i, j in _SYM_IJ]
+            avg += sig
+            W += float(np.sum(sig * eps)) * abs(np.linalg.det(J)) * w
+            if q == 0:
+                vm_q1[e] = von_mises(sig)
+        avg /= len(qps)
+        vm_avg[e] = von_mises(avg)
+        energy[e] = 0.5 * W
+        if vm_avg[e] > max_vm:  # strict: first cell wins ties (:586)
+            max_vm, max_cell = vm_avg[e], e
+    return dict(sigma=sigma, vm_avg=vm_avg, max_vm=max_vm, max_cell=max_cell, vm_q1=vm_q1, element_energy=energy)
 
 
 # --------------------------------------------------------------------------------------

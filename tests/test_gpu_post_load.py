@@ -1,0 +1,230 @@
+"""-m gpu parity tests of the density-dependent body force inside the loop (Optimization.jl:300-311, FEA.jl:486-526)
+and of the post-solve stress fields the export branches use (FEA.jl:566-597, PostProcessing.jl:172-222), through the
+C ABI against the oracle.  Tolerances: cell fields 1e-10 relative (north_star: sensitivities / filters class),
+loop compliance 1e-6 relative, densities 1e-3."""
+import numpy as np
+import pytest
+
+from oracle import simp_oracle as o
+from test_gpu_unstructured import MESHES, bc_and_load
+from test_gpu_unstructured import make_ctx as make_um_ctx
+
+pytestmark = pytest.mark.gpu
+
+
+def relmax(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def clamp_xmin(g, dofs):
+    return np.sort(dofs[np.array(sorted(o.select_nodes_by_plane(g, [0, 0, 0], [1, 0, 0], 1e-6)))].ravel())
+
+
+def structured_ctx(factory, g, dofs, pres=None, **params):
+    nx, ny, nz, left, right = g.structured
+    ctx = factory()
+    if params:
+        ctx.set_params(**params)
+    ctx.set_grid_structured(nx, ny, nz, (right[0] - left[0]) / nx, (right[1] - left[1]) / ny, (right[2] - left[2]) / nz, dofs)
+    if pres is not None:
+        ctx.set_dirichlet(pres)
+    return ctx
+
+
+def densities_with_voids(n, seed):
+    """physical densities in (0, 1] with some cells below / at / just above the 1e-6 skip threshold (FEA.jl:495-497)"""
+    rng = np.random.default_rng(seed)
+    rho = 1e-3 + (1 - 1e-3) * rng.random(n)
+    rho[rng.choice(n, size=max(1, n // 7), replace=False)] = 1e-9
+    rho[0] = 1e-6
+    rho[n - 1] = 0.999e-6
+    return rho
+
+
+GRIDS = [((13, 7, 5), (13.0, 3.5, 1.25)), ((12, 6, 4), (0.6, 0.3, 0.2)), ((1, 1, 1), (1.0, 1.0, 1.0)), ((3, 18, 17), (3.0, 18.0, 17.0))]
+SMALL_MESHES = ["shuffled_jittered_hex", "hex_split_into_tets", "cantilever_beam_vtu"]
+
+
+@pytest.mark.parametrize("nel,right", GRIDS)
+def test_body_force_structured_matches_oracle(gpu_ctx_factory, nel, right):
+    g = o.generate_grid_hex(nel, (0.0, 0.0, 0.0), right)
+    dofs = o.distribute_dofs(g)
+    ctx = structured_ctx(gpu_ctx_factory, g, dofs, clamp_xmin(g, dofs))
+    b = np.array([0.3, -9.81, 2.5])
+    for base in (1.0, 7850.0):
+        dens = densities_with_voids(g.n_cells, 3) * base
+        ref = o.body_force(g, dofs, b, dens)
+        got = ctx.body_force(b, dens)
+        assert relmax(got, ref) < 1e-12
+        # total applied force = b * sum of the masses that were not skipped
+        V = o.element_volumes(g)
+        mass = float(np.sum(dens[dens >= 1e-6] * V[dens >= 1e-6]))
+        assert np.allclose([got[dofs[:, c]].sum() for c in range(3)], b * mass, rtol=1e-11, atol=1e-300)
+
+
+@pytest.mark.parametrize("mesh", SMALL_MESHES)
+def test_body_force_unstructured_matches_oracle(gpu_ctx_factory, golden_dir, mesh):
+    g = MESHES[mesh](golden_dir)
+    dofs = o.distribute_dofs(g)
+    pres, _ = bc_and_load(g, dofs)
+    ctx = make_um_ctx(gpu_ctx_factory, g, dofs, pres)
+    b = np.array([0.3, -9.81, 2.5])
+    dens = densities_with_voids(g.n_cells, 4) * 2700.0
+    assert relmax(ctx.body_force(b, dens), o.body_force(g, dofs, b, dens)) < 1e-12
+
+
+def _check_stress(ctx, g, dofs, rho, u, nu=0.3, E0=1.0, Emin=1e-9, p=3.0):
+    ref = o.stresses_simp(g, dofs, u, E0, nu, Emin, p, rho)
+    ctx.set_density(rho)
+    ctx.set_displacement(u)
+    got = ctx.stress_fields()
+    assert relmax(got["vm_q1"], ref["vm_q1"]) < 1e-10
+    assert relmax(got["vm_avg"], ref["vm_avg"]) < 1e-10
+    assert relmax(got["element_energy"], ref["element_energy"]) < 1e-10
+    assert abs(got["max_vm"] - ref["max_vm"]) <= 1e-12 * ref["max_vm"]
+    assert got["max_cell"] == ref["max_cell"]
+    # scalars only (the loop's export branch can skip the downloads)
+    light = ctx.stress_fields(want_fields=False)
+    assert light["vm_q1"] is None and light["max_cell"] == ref["max_cell"] and light["max_vm"] == got["max_vm"]
+    # the Gauss-point tensors themselves, whole mesh and a chunk in the middle
+    nq = ctx.stress_nq
+    assert ref["sigma"].shape[1] == nq
+    sig = ctx.stress_tensors()
+    assert sig.shape == ref["sigma"].shape and relmax(sig, ref["sigma"]) < 1e-10
+    if g.n_cells >= 4:
+        c0, n = g.n_cells // 3, g.n_cells // 2
+        assert np.array_equal(ctx.stress_tensors(c0, n), sig[c0:c0 + n])
+    # element energies add up to the strain energy 1/2 u'K u of the unconstrained operator
+    k0 = o.unit_element_matrices(g, nu, 1.0)
+    ee = 0.5 * o.simp_modulus(rho, E0, Emin, p) * o.element_energies(g, dofs, u, k0)
+    assert relmax(got["element_energy"], ee) < 1e-10
+
+
+@pytest.mark.parametrize("nel,right", GRIDS)
+def test_stress_fields_structured_match_oracle(gpu_ctx_factory, nel, right):
+    g = o.generate_grid_hex(nel, (0.0, 0.0, 0.0), right)
+    dofs = o.distribute_dofs(g)
+    rng = np.random.default_rng(11)
+    ctx = structured_ctx(gpu_ctx_factory, g, dofs, clamp_xmin(g, dofs))
+    _check_stress(ctx, g, dofs, densities_with_voids(g.n_cells, 5), rng.standard_normal(3 * g.n_nodes))
+
+
+def test_stress_fields_zero_displacement(gpu_ctx_factory):
+    """all von Mises values 0: the reference's `> max` never fires and the cell id stays 'none' (FEA.jl:569-589)"""
+    g = o.generate_grid_hex((4, 3, 2), (0.0, 0.0, 0.0), (4.0, 3.0, 2.0))
+    dofs = o.distribute_dofs(g)
+    ctx = structured_ctx(gpu_ctx_factory, g, dofs, clamp_xmin(g, dofs))
+    ctx.set_density(np.full(g.n_cells, 0.5))
+    ctx.set_displacement(np.zeros(3 * g.n_nodes))
+    got = ctx.stress_fields()
+    assert got["max_vm"] == 0.0 and got["max_cell"] == -1 and not got["vm_avg"].any() and not got["element_energy"].any()
+    # rigid translation: no strain either
+    u = np.zeros(3 * g.n_nodes)
+    u[dofs[:, 1]] = 0.25
+    ctx.set_displacement(u)
+    assert ctx.stress_fields()["vm_q1"].max() < 1e-15
+
+
+@pytest.mark.parametrize("mesh", SMALL_MESHES)
+def test_stress_fields_unstructured_match_oracle(gpu_ctx_factory, golden_dir, mesh):
+    g = MESHES[mesh](golden_dir)
+    dofs = o.distribute_dofs(g)
+    pres, _ = bc_and_load(g, dofs)
+    ctx = make_um_ctx(gpu_ctx_factory, g, dofs, pres)
+    rng = np.random.default_rng(12)
+    _check_stress(ctx, g, dofs, densities_with_voids(g.n_cells, 6), rng.standard_normal(int(dofs.max()) + 1))
+
+
+@pytest.mark.parametrize("precond", [0, 1])
+def test_loop_with_body_force_matches_oracle(gpu_ctx_factory, precond):
+    """simp_optimize(..., acceleration_data) (Optimization.jl:300-311, :517-528): self-weight plus the tip load"""
+    nel = (24, 8, 4)
+    g, dofs, f, pres = o.cantilever_problem(nel)
+    accel, base = np.array([0.0, -9.81, 0.0]), 2.0e-3
+    prm = o.OptimizationParameters(volume_fraction=0.4, max_iterations=8, tolerance=0.0)
+    ref = o.simp_optimize(g, dofs, f, pres, prm, acceleration_data=(accel, base))
+    plain = o.simp_optimize(g, dofs, f, pres, prm)
+    assert abs(ref["history"][0].energy / plain["history"][0].energy - 1.0) > 1e-3  # the body force matters in this case
+    R = 1.5 * o.estimate_element_size(g)
+    ctx = structured_ctx(gpu_ctx_factory, g, dofs, pres, volume_fraction=0.4, filter_radius=R, pcg_rtol=1e-10, pcg_check_every=10,
+                         precond=precond)
+    ctx.set_load(f)
+    ctx.set_body_force(accel, base)
+    ctx.filter_build_structured()
+    ctx.init_design(None)
+    stats = [ctx.iterate() for _ in range(8)]
+    e_ref = np.array([h.energy for h in ref["history"]])
+    assert np.max(np.abs(np.array([s.energy for s in stats]) - e_ref) / e_ref) < 1e-6
+    e_fin, v_fin, _ = ctx.final_analysis()
+    assert abs(e_fin - ref["energy"]) / ref["energy"] < 1e-6
+    assert np.abs(ctx.get_physical_density() - ref["densities"]).max() < 1e-3
+    # switching it off restores the load-only right-hand side
+    ctx.set_body_force(None)
+    ctx.init_design(None)
+    s0 = ctx.iterate()
+    assert abs(s0.energy - plain["history"][0].energy) / plain["history"][0].energy < 1e-6
+
+
+def test_body_force_only_unstructured_loop(gpu_ctx_factory, golden_dir):
+    """a body force alone is a valid right-hand side (no esimp_set_load); imported mesh, density filter"""
+    g = MESHES["shuffled_jittered_hex"](golden_dir)
+    dofs = o.distribute_dofs(g)
+    pres, _ = bc_and_load(g, dofs)
+    accel, base = np.array([0.0, -1.0, 0.5]), 1.0
+    prm = o.OptimizationParameters(volume_fraction=0.4, max_iterations=5, tolerance=0.0, filter_radius=1.5, filter_type="density")
+    ref = o.simp_optimize(g, dofs, np.zeros(int(dofs.max()) + 1), pres, prm, acceleration_data=(accel, base))
+    V = o.element_volumes(g)
+    fc = o.create_filter_cache(g, 1.5, V)
+    ctx = make_um_ctx(gpu_ctx_factory, g, dofs, pres, volume_fraction=0.4, filter_type=1, pcg_rtol=1e-10, pcg_check_every=20)
+    ctx.set_body_force(accel, base)
+    ctx.filter_build_csr(fc.rowptr, fc.col, fc.centers, V, fc.radius)
+    ctx.init_design(None)
+    stats = [ctx.iterate() for _ in range(5)]
+    e_ref = np.array([h.energy for h in ref["history"]])
+    assert np.max(np.abs(np.array([s.energy for s in stats]) - e_ref) / e_ref) < 1e-6
+    e_fin, _, _ = ctx.final_analysis()
+    assert abs(e_fin - ref["energy"]) / ref["energy"] < 1e-6
+    assert np.abs(ctx.get_physical_density() - ref["densities"]).max() < 1e-3
+
+
+def test_host_api_acceleration_and_stresses():
+    """The reference-shaped calls: simp_optimize(...; acceleration_data), calculate_stresses_simp,
+    apply_variable_density_volume_force!, create_results_data."""
+    import easysimp_b200 as es
+
+    nel = (24, 8, 4)
+    grid = es.generate_grid(es.Hexahedron, nel, (0.0, 0.0, 0.0), (24.0, 8.0, 4.0))
+    dh, cellvalues, K, f = es.setup_problem(grid, device=0)
+    fixed = es.select_nodes_by_plane(grid, [0.0, 0.0, 0.0], [1.0, 0.0, 0.0], 1e-3)
+    force = es.select_nodes_by_circle(grid, [24.0, 0.0, 2.0], [1.0, 0.0, 0.0], 1.0)
+    mm = es.create_simp_material_model(1.0, 0.3, 1e-9, 3.0)
+    es.assemble_stiffness_matrix_simp_(K, f, dh, cellvalues, mm, np.full(grid.getncells(), 0.4))
+    ch = es.apply_fixed_boundary_(K, f, dh, fixed)
+    accel, base = [0.0, -9.81, 0.0], 2.0e-3
+    params = es.OptimizationParameters(volume_fraction=0.4, max_iterations=6, tolerance=0.0, pcg_rtol=1e-10, tolerance_checkpoints=[0.5])
+    res = es.simp_optimize(grid, dh, cellvalues, [es.PointLoad(dh, sorted(force), [0.0, -1.0, 0.0])], [ch], params,
+                           acceleration_data=(accel, base), K=K)
+    g, dofs, fo, pres = o.cantilever_problem(nel)
+    ref = o.simp_optimize(g, dofs, fo, pres, o.OptimizationParameters(volume_fraction=0.4, max_iterations=6, tolerance=0.0),
+                          acceleration_data=(np.array(accel), base))
+    e_ref = np.array([h.energy for h in ref["history"]])
+    assert np.max(np.abs(np.array(res.energy_history) - e_ref) / e_ref) < 1e-6
+    assert np.abs(res.densities - ref["densities"]).max() < 1e-3
+    # OptimizationResult.stresses (Optimization.jl:537-539) against the oracle on the library's own final state
+    sref = o.stresses_simp(g, dofs, res.displacements, 1.0, 0.3, 1e-9, 3.0, res.densities)
+    st = res.stresses
+    assert len(st) == g.n_cells and relmax(st.von_mises_q1, sref["vm_q1"]) < 1e-10 and relmax(st.von_mises_avg, sref["vm_avg"]) < 1e-10
+    assert st.max_cell == sref["max_cell"] and relmax(st[st.max_cell], sref["sigma"][st.max_cell]) < 1e-10
+    assert 0.5 in res.checkpoints and len(res.checkpoints[0.5]["stresses"]) == g.n_cells
+    data = es.create_results_data(grid, dh, cellvalues, res)
+    assert relmax(data["element_energy"], sref["element_energy"]) < 1e-10 and data["displacement"].shape == (3, g.n_nodes)
+    assert abs(data["element_energy"].sum() - res.energy) < 1e-6 * res.energy  # constrained dofs carry u = 0
+    # stand-alone forms with host arrays
+    rho = densities_with_voids(g.n_cells, 9)
+    fb = es.apply_variable_density_volume_force_(np.zeros(dh.ndofs), dh, cellvalues, accel, rho * 7850.0)
+    assert relmax(fb, o.body_force(g, dofs, np.array(accel), rho * 7850.0)) < 1e-12
+    u = np.random.default_rng(3).standard_normal(dh.ndofs)
+    sf, vmax, cell = es.calculate_stresses_simp(u, dh, cellvalues, mm, rho)
+    sref = o.stresses_simp(g, dofs, u, 1.0, 0.3, 1e-9, 3.0, rho)
+    assert cell == sref["max_cell"] and abs(vmax - sref["max_vm"]) <= 1e-12 * vmax and relmax(sf.tensors(), sref["sigma"]) < 1e-10
+    K.ctx.close()
