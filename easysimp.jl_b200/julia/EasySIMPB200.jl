@@ -134,15 +134,20 @@ end
     simp_optimize_b200(grid, dh, cellvalues, loads, boundary_conditions, params, acceleration_data = nothing)
 
 Same contract as `simp_optimize` (Optimization.jl:178-565).  The loop body (:273-379) is ONE ccall per iteration;
-density, displacement and sensitivities stay on the GPU.  Export / checkpoint branches (:407-477) download the two
-fields they need and then run the reference's unchanged host code.
+density, displacement and sensitivities stay on the GPU.  `acceleration_data` (:300-311) becomes one
+`esimp_set_body_force` call; export / checkpoint branches (:407-477) read the von Mises / element-energy cell arrays from
+`stress_fields_b200` instead of walking a Dict of tensors.
 """
 function simp_optimize_b200(grid::Grid, dh::DofHandler, cellvalues, loads, boundary_conditions,
                             params::OptimizationParameters, acceleration_data = nothing; device::Integer = -1)
-    acceleration_data === nothing || error("variable-density body force stays on the reference path (SURVEY 8f-4)")
     volumes = calculate_element_volumes(grid, create_volume_quadrature(grid))
     fc = create_filter_cache(grid, params.filter_radius, volumes)
     ctx = configure!(Context(device), grid, dh, loads, boundary_conditions, params, fc)
+    if acceleration_data !== nothing   # (acceleration_vector, base_density): f += rho_e * base * b * int N on every assembly
+        acc, base = acceleration_data
+        check(ctx, ccall((:esimp_set_body_force, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Cdouble), ctx.ptr,
+                         Float64[acc[1], acc[2], acc[3]], Float64(base)), "esimp_set_body_force")
+    end
     check(ctx, ccall((:esimp_init_design, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), ctx.ptr, C_NULL), "esimp_init_design")
     energy_history, volume_history = Float64[], Float64[]
     converged, iteration = false, 0
@@ -154,7 +159,7 @@ function simp_optimize_b200(grid::Grid, dh::DofHandler, cellvalues, loads, bound
         push!(energy_history, s.energy); push!(volume_history, s.volume)
         # logger / @printf / tolerance_checkpoints / export_interval exactly as Optimization.jl:382-477, using
         # s.energy, s.volume, s.change, s.lambda, s.grayness, s.max_u and (only when exporting)
-        # esimp_get_physical_density / esimp_get_displacement
+        # esimp_get_physical_density / esimp_get_displacement / stress_fields_b200(ctx)
         if s.change < params.tolerance
             converged = true
             break
@@ -166,9 +171,34 @@ function simp_optimize_b200(grid::Grid, dh::DofHandler, cellvalues, loads, bound
     rho = zeros(getncells(grid)); u = zeros(ndofs(dh))
     check(ctx, ccall((:esimp_get_physical_density, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), ctx.ptr, rho), "esimp_get_physical_density")
     check(ctx, ccall((:esimp_get_displacement, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), ctx.ptr, u), "esimp_get_displacement")
-    mm = create_simp_material_model(params.E0, params.ν, params.Emin, params.p)
-    stress_field, _, _ = calculate_stresses_simp(u, dh, cellvalues, mm, rho)   # stays on the host (FEA.jl:537-597)
+    stress_field = stress_fields_b200(ctx)   # :537-539 on the device state the final analysis left
     return OptimizationResult(rho, u, stress_field, e[], v[], iteration, converged, energy_history, volume_history)
+end
+
+"""
+    stress_fields_b200(ctx) -> (von_mises, von_mises_avg, element_energy, max_von_mises, max_cell)
+
+`calculate_stresses_simp` (FEA.jl:566-597) + `calculate_von_mises_stresses` / `calculate_element_energy`
+(PostProcessing.jl:172-222) for the displacement and physical densities the context holds.  `von_mises` is the exported
+field (first Gauss point), `max_von_mises` / `max_cell` (1-based, 0 = none) are those of the Gauss-point average.
+`stress_tensors_b200(ctx, cells)` returns the Dict entries themselves for a range of cells.
+"""
+function stress_fields_b200(ctx::Context)
+    n = Int(ccall((:esimp_n_cells, LIB), Int64, (Ptr{Cvoid},), ctx.ptr))
+    vm, vma, ee = zeros(n), zeros(n), zeros(n)
+    mx, cell = Ref{Cdouble}(0), Ref{Int64}(-1)
+    check(ctx, ccall((:esimp_stress_fields, LIB), Cint,
+                     (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}, Ref{Cdouble}, Ref{Int64}),
+                     ctx.ptr, vm, vma, ee, mx, cell), "esimp_stress_fields")
+    return (von_mises = vm, von_mises_avg = vma, element_energy = ee, max_von_mises = mx[], max_cell = cell[] + 1)
+end
+
+function stress_tensors_b200(ctx::Context, cells::UnitRange{Int})
+    nq = Int(ccall((:esimp_stress_nq, LIB), Cint, (Ptr{Cvoid},), ctx.ptr))
+    sig = zeros(6, nq, length(cells))   # column-major view of the library's [cell][q][6]
+    check(ctx, ccall((:esimp_stress_tensors, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Cdouble}),
+                     ctx.ptr, first(cells) - 1, length(cells), sig), "esimp_stress_tensors")
+    return Dict(c => [SymmetricTensor{2,3,Float64}(Tuple(sig[:, q, i])) for q in 1:nq] for (i, c) in enumerate(cells))
 end
 
 """
@@ -190,6 +220,6 @@ function Base.:*(op::Context, u::Vector{Float64})
     return y
 end
 
-export Context, simp_optimize_b200, assemble_stiffness_matrix_simp!
+export Context, simp_optimize_b200, assemble_stiffness_matrix_simp!, stress_fields_b200, stress_tensors_b200
 
 end # module
