@@ -123,7 +123,7 @@ int esimp_create(esimp_ctx** out, int device) {
     if (const char* e = getenv("ESIMP_MG_REPLICATE_CELLS")) ctx->mg_replicate_cells = atoll(e);
     auto bail = [&](const char* what) {
         std::string msg = std::string(what) + ": " + cudaGetErrorString(cudaGetLastError());
-        delete ctx;
+        esimp_destroy(ctx);  // frees whatever was created so far
         return esimp_fail(nullptr, ESIMP_ERR_CUDA, msg);
     };
     if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice");

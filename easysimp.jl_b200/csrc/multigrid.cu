@@ -13,8 +13,13 @@
 //     iterations per level and SIMP iteration; pre- and post-smoothing use the same polynomial, so the
 //     V-cycle is symmetric positive definite and plain PCG applies;
 //   * coarsest level: mg_coarse_its Chebyshev iterations.
+//   * with the default operator variant the Chebyshev update z' = z + c1 d + c2 Dinv (r - A z), the residual
+//     r - A z and the <r, z> of the outer CG are fused into the store phase of the operator kernel
+//     (FUSE_SMOOTH / FUSE_RESID / FUSE_SMOOTH_DOT modes); k_cheb_step / k_residual serve the other variants.
 // x-slab partition: level l of rank r is the slab [ex0/2^l, ex1/2^l); the same one-plane node halo and
-// one-layer cell halo (comm.cu) are used on every level.
+// one-layer cell halo (comm.cu) are used on every level.  Levels with at most mg_replicate_cells cells are
+// REPLICATED on every rank instead (one allreduce of the restricted residual at the transition, no
+// communication below): deep levels are latency bound, not bandwidth bound.
 // Prototype + convergence study: scripts/gmg_prototype.py (27-58 iterations where Jacobi-PCG needs 500-1200).
 #include <math.h>
 #include <stdio.h>
