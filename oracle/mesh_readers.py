@@ -26,7 +26,8 @@ def _appended_array(blob, offset, dtype):
     return np.frombuffer(bytes(out), dtype=_DT[dtype])
 
 
-def read_vtu(path):
+def read_vtu_arrays(path):
+    """Every appended DataArray of the file by name (Points, connectivity, ..., and any cell / point data)."""
     raw = open(path, "rb").read()
     head_end = raw.index(b"<AppendedData")
     head = raw[:head_end].decode("utf-8", "replace")
@@ -36,6 +37,11 @@ def read_vtu(path):
     arrays = {}
     for m in re.finditer(r'<DataArray type="(\w+)" Name="(\w+)"[^>]*offset="(\d+)"', head):
         arrays[m.group(2)] = _appended_array(blob, int(m.group(3)), m.group(1))
+    return arrays
+
+
+def read_vtu(path):
+    arrays = read_vtu_arrays(path)
     pts = arrays["Points"].reshape(-1, 3).astype(np.float64)
     conn, offs, types = arrays["connectivity"].astype(np.int64), arrays["offsets"].astype(np.int64), arrays["types"]
     starts = np.concatenate([[0], offs[:-1]])
