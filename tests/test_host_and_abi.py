@@ -91,6 +91,42 @@ def test_structured_dof_numbering_closed_form(nel):
     assert np.array_equal(want[go.cells[0]].ravel(), np.arange(24))
 
 
+def test_host_constraint_handlers_fixed_and_sliding():
+    """apply_fixed_boundary! / apply_sliding_boundary! (FEA.jl:293-340): prescribed dofs per handler, 1-based
+    directions, f zeroed there, and the operator handle receives the UNION of all handlers (Optimization.jl:581-583)."""
+    from easysimp_b200.host import DofHandler, _distribute_dofs
+
+    class FakeCtx:
+        def __init__(self):
+            self.calls = []
+
+        def set_dirichlet(self, dofs):
+            self.calls.append(np.array(dofs))
+
+    class FakeK:
+        def __init__(self):
+            self.ctx, self.prescribed, self._density = FakeCtx(), np.zeros(0, dtype=np.int64), None
+
+    g = es.generate_grid(es.Hexahedron, (4, 3, 2))
+    dh = DofHandler(g, _distribute_dofs(g))
+    K, f = FakeK(), np.ones(dh.ndofs)
+    left = es.select_nodes_by_plane(g, [0.0, 0.0, 0.0], [1.0, 0.0, 0.0], 1e-6)
+    bottom = es.select_nodes_by_plane(g, [0.0, 0.0, 0.0], [0.0, 1.0, 0.0], 1e-6)
+    ch1 = es.apply_sliding_boundary_(K, f, dh, left, [1])
+    assert np.array_equal(ch1.prescribed_dofs, np.sort(dh.dof_of_node[sorted(left), 0]))
+    ch2 = es.apply_sliding_boundary_(K, f, dh, bottom, [2, 3])
+    assert np.array_equal(ch2.prescribed_dofs, np.sort(dh.dof_of_node[sorted(bottom)][:, 1:].ravel()))
+    ch3 = es.apply_fixed_boundary_(K, f, dh, {0})
+    assert np.array_equal(ch3.prescribed_dofs, np.sort(dh.dof_of_node[0]))
+    union = np.unique(np.concatenate([ch1.prescribed_dofs, ch2.prescribed_dofs, ch3.prescribed_dofs]))
+    assert np.array_equal(K.prescribed, union) and np.array_equal(K.ctx.calls[-1], union) and len(K.ctx.calls) == 3
+    assert not f[union].any() and f.sum() == dh.ndofs - union.size
+    # reference-side oracle statement of the same sets
+    go = o.generate_grid_hex((4, 3, 2))
+    do = o.distribute_dofs(go)
+    assert np.array_equal(ch1.prescribed_dofs, np.sort(do[sorted(o.select_nodes_by_plane(go, [0, 0, 0], [1, 0, 0], 1e-6)), 0]))
+
+
 def test_host_node_selection_matches_reference_recipe():
     g = es.generate_grid(es.Hexahedron, (60, 20, 4), (0, 0, 0), (60.0, 20.0, 4.0))
     fixed = es.select_nodes_by_plane(g, [0.0, 0.0, 0.0], [1.0, 0.0, 0.0], 1e-3)
