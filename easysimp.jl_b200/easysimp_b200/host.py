@@ -394,6 +394,29 @@ def calculate_element_volumes(grid: Grid):
     return vol
 
 
+def check_sensitivity_health(sensitivities) -> bool:
+    """check_sensitivity_health (OptimalityCriteria.jl:19-40): the warn-only diagnostic the reference runs at the top
+    of every OC update.  It never changes a result, so the device loop skips it; this is the same test for callers who
+    want it on sensitivities they downloaded (`Context.sensitivities()`, `Context.filter_sens(...)`)."""
+    import warnings
+
+    s = np.asarray(sensitivities, dtype=np.float64)
+    if np.count_nonzero(s < 0) < s.size * 0.5:
+        warnings.warn("Less than 50% of sensitivities are negative. Check if energy sensitivities are computed correctly.")
+        return False
+    a = np.abs(s)
+    med = float(np.median(a))
+    eps = float(np.finfo(np.float64).eps)
+    if med < eps:
+        warnings.warn(f"Sensitivities are effectively zero (median: {med}).")
+        return False
+    ratio = float(a.max()) / max(med, eps)
+    if ratio > 1e8:
+        warnings.warn(f"Sensitivity range too large (max/median: {ratio}). Check problem scaling.")
+        return False
+    return True
+
+
 # ----------------------------------------------------------------------------- parameters / result
 @dataclass
 class OptimizationParameters:

@@ -127,6 +127,26 @@ def test_host_constraint_handlers_fixed_and_sliding():
     assert np.array_equal(ch1.prescribed_dofs, np.sort(do[sorted(o.select_nodes_by_plane(go, [0, 0, 0], [1, 0, 0], 1e-6)), 0]))
 
 
+def test_check_sensitivity_health_conditions():
+    """the three warn-only conditions of OptimalityCriteria.jl:19-40, in the reference's order"""
+    import warnings
+
+    rng = np.random.default_rng(0)
+    good = -rng.random(1001) - 0.1
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        assert es.check_sensitivity_health(good) is True
+    for bad, msg in ((np.abs(good), "negative"), (np.where(np.arange(1001) < 400, good, -1e-20), "effectively zero"),
+                     (np.concatenate([good, [-1e9]]), "range too large")):
+        with pytest.warns(UserWarning, match=msg):
+            assert es.check_sensitivity_health(bad) is False
+    # exactly half negative passes the first test (strict <), and is then judged by the median
+    half = np.concatenate([-np.ones(500), np.ones(500)])
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        assert es.check_sensitivity_health(half) is True
+
+
 def test_host_node_selection_matches_reference_recipe():
     g = es.generate_grid(es.Hexahedron, (60, 20, 4), (0, 0, 0), (60.0, 20.0, 4.0))
     fixed = es.select_nodes_by_plane(g, [0.0, 0.0, 0.0], [1.0, 0.0, 0.0], 1e-3)
