@@ -546,11 +546,12 @@ static int launch_fused_t(esimp_ctx* ctx, const OpView& vw, const double* d_in, 
     if (ctx->fused_chunk > 0) chunk = ctx->fused_chunk;
     const int nchunk = (nplanes + chunk - 1) / chunk;
     const size_t smem = sizeof(FusedSmem<TY, TZ, (MODE == FUSE_SMOOTH || MODE == FUSE_SMOOTH_DOT) ? 3 : (MODE == FUSE_RESID ? 1 : 0)>);
-    static bool attr_set = false;
+    static unsigned long long attr_devices = 0;  // the attribute is per device: one bit per device this process has used
     auto kern = k_matvec_fused<TY, TZ, ATOMIC, MINB, MODE>;
-    if (!attr_set) {
+    const unsigned long long dev_bit = 1ull << (ctx->device & 63);
+    if (!(attr_devices & dev_bit)) {
         ESIMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        attr_devices |= dev_bit;
     }
     if (ATOMIC) {
         k_zero_perimeter<TY, TZ><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(g, vw.own_p0, vw.own_p1, d_out);
