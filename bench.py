@@ -41,7 +41,8 @@ def parse():
     ap.add_argument("--filter-radius", type=float, default=1.5)
     ap.add_argument("--volfrac", type=float, default=0.5)
     ap.add_argument("--variant", type=int, default=0)
-    ap.add_argument("--precond", default="gmg", choices=["jacobi", "gmg"])
+    ap.add_argument("--precond", default="gmg", choices=["jacobi", "gmg", "gmg32"],
+                    help="gmg32 = the V-cycle evaluated in fp32 inside the fp64 CG (opt-in, csrc/multigrid32.cu)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -175,7 +176,8 @@ def workload_config(args, nel, pcg_iters, pcg_note):
             "volume_fraction": args.volfrac, "p": 3.0, "E0": 1.0, "Emin": 1e-9, "nu": 0.3, "filter": "sensitivity",
             "filter_radius": args.filter_radius, "move_limit": 0.2, "damping": 0.5,
             "solver": ("CG fp64 + geometric-multigrid V(2,2) Chebyshev-Jacobi preconditioner" if args.precond == "gmg" and args.impl == "b200"
-                       else "Jacobi-PCG fp64") + ", warm start",
+                       else "CG fp64 + geometric-multigrid V(2,2) Chebyshev-Jacobi preconditioner evaluated in fp32"
+                       if args.precond == "gmg32" and args.impl == "b200" else "Jacobi-PCG fp64") + ", warm start",
             "pcg_rtol": args.pcg_rtol, "mean_pcg_iters_per_step": pcg_iters, "pcg_iters_source": pcg_note,
             "partition": f"x-slabs over {args.gpus} GPU(s)", "l2": "inputs_larger_than_l2 (813 MB per vector vs 126 MB L2)"}
 
@@ -201,7 +203,7 @@ def run_b200(args):
     pres, f = cantilever(nel)
     ctx = es.Context(local)
     ctx.set_params(volume_fraction=args.volfrac, filter_radius=args.filter_radius, pcg_rtol=args.pcg_rtol, pcg_maxit=200000,
-                   pcg_check_every=50, matvec_variant=args.variant, warm_start=1, precond=int(args.precond == "gmg"))
+                   pcg_check_every=50, matvec_variant=args.variant, warm_start=1, precond={"jacobi": 0, "gmg": 1, "gmg32": 2}[args.precond])
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:

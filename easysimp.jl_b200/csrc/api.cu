@@ -184,7 +184,8 @@ int esimp_set_params(esimp_ctx* ctx, const esimp_params* p) {
     if (!p) return esimp_fail(ctx, ESIMP_ERR_ARG, "params is NULL");
     if (!(p->nu > -1.0 && p->nu < 0.5) || !(p->E0 > 0) || !(p->p >= 1.0)) return esimp_fail(ctx, ESIMP_ERR_ARG, "invalid material parameters");
     bool nu_changed = p->nu != ctx->prm.nu;
-    if (p->precond != ESIMP_PRECOND_JACOBI && p->precond != ESIMP_PRECOND_GMG) return esimp_fail(ctx, ESIMP_ERR_ARG, "unknown preconditioner");
+    if (p->precond != ESIMP_PRECOND_JACOBI && p->precond != ESIMP_PRECOND_GMG && p->precond != ESIMP_PRECOND_GMG_FP32)
+        return esimp_fail(ctx, ESIMP_ERR_ARG, "unknown preconditioner");
     bool r_changed = p->filter_radius != ctx->prm.filter_radius;
     ctx->prm = *p;
     if (nu_changed) {
@@ -416,7 +417,7 @@ static int prepare_operator(esimp_ctx* ctx) {
         ESIMP_TRY(hex8_diagonal(ctx));
     else
         ESIMP_TRY(um_diagonal(ctx));
-    if (ctx->prm.precond == ESIMP_PRECOND_GMG && ctx->structured) ESIMP_TRY(mg_setup(ctx));
+    if ((ctx->prm.precond == ESIMP_PRECOND_GMG || ctx->prm.precond == ESIMP_PRECOND_GMG_FP32) && ctx->structured) ESIMP_TRY(mg_setup(ctx));
     ESIMP_TRY(body_force_refresh_rhs(ctx));  // Optimization.jl:300-311
     ctx->density_set = true;
     return ESIMP_OK;
@@ -465,6 +466,7 @@ static int solve_internal(esimp_ctx* ctx, int* iters, double* relres) {
     if (!ctx->prm.warm_start) ESIMP_CUDA(cudaMemsetAsync(ctx->d_u, 0, sizeof(double) * ctx->ndof_loc, ctx->stream));
     ESIMP_TRY(mask_rhs_and_guess(ctx));
     if (ctx->prm.precond == ESIMP_PRECOND_GMG && ctx->structured) return pcg_solve_mg(ctx, iters, relres);
+    if (ctx->prm.precond == ESIMP_PRECOND_GMG_FP32 && ctx->structured) return pcg_solve_mg32(ctx, iters, relres);
     return pcg_solve(ctx, iters, relres);
 }
 

@@ -124,6 +124,27 @@ int comm_halo_nodes_lv(esimp_ctx* ctx, const GridDev& g, int own_p0, int own_p1,
     ESIMP_NCCL(g_nccl.GroupEnd());
     return ESIMP_OK;
 }
+int comm_allreduce_f32(esimp_ctx* ctx, float* d_buf, long long n) {
+    if (ctx->nranks <= 1) return ESIMP_OK;
+    ESIMP_NCCL(g_nccl.AllReduce(d_buf, d_buf, (size_t)n, ncclFloat, ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
+    return ESIMP_OK;
+}
+int comm_halo_nodes_lv_f32(esimp_ctx* ctx, const GridDev& g, int own_p0, int own_p1, bool has_left, bool has_right, float* v) {
+    if (ctx->nranks <= 1) return ESIMP_OK;
+    ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    const size_t np = (size_t)3 * g.plane;
+    ESIMP_NCCL(g_nccl.GroupStart());
+    if (has_left) {
+        ESIMP_NCCL(g_nccl.Send(v + (size_t)own_p0 * np, np, ncclFloat, ctx->rank - 1, comm, ctx->stream));
+        ESIMP_NCCL(g_nccl.Recv(v, np, ncclFloat, ctx->rank - 1, comm, ctx->stream));
+    }
+    if (has_right) {
+        ESIMP_NCCL(g_nccl.Send(v + (size_t)(own_p1 - 1) * np, np, ncclFloat, ctx->rank + 1, comm, ctx->stream));
+        ESIMP_NCCL(g_nccl.Recv(v + (size_t)(g.NPX - 1) * np, np, ncclFloat, ctx->rank + 1, comm, ctx->stream));
+    }
+    ESIMP_NCCL(g_nccl.GroupEnd());
+    return ESIMP_OK;
+}
 int comm_halo_nodes(esimp_ctx* ctx, double* v) {
     return comm_halo_nodes_lv(ctx, ctx->g, ctx->own_p0, ctx->own_p1, ctx->has_left, ctx->has_right, v);
 }

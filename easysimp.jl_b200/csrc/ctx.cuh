@@ -77,6 +77,8 @@ struct MGLevel {
     bool pi_valid = false;
     bool owns = false;
     bool replicated = false;  // multi-rank: every rank holds the whole (small) grid of this level, no communication
+    // single-precision mirror of the level for the FP32 V-cycle (multigrid32.cu; allocated on first use)
+    float *f_E = nullptr, *f_dinv = nullptr, *f_r = nullptr, *f_z = nullptr, *f_z2 = nullptr, *f_d = nullptr, *f_q = nullptr;
 };
 
 struct UnstructuredMesh {
@@ -218,6 +220,11 @@ int hex8_diagonal_view(esimp_ctx* ctx, const OpView& vw, double* dinv, long long
 int hex8_smooth_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double* z_out, const double* r, const double* dinv,
                      double* d, double c1, double c2, int dot_slot = -1);
 int hex8_resid_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double* res_out, const double* r);
+int hex8_smooth_view_f32(esimp_ctx* ctx, const OpView& vw, const float* E, const float* z_in, float* z_out, const float* r,
+                         const float* dinv, float* d, float c1, float c2);
+int hex8_resid_view_f32(esimp_ctx* ctx, const OpView& vw, const float* E, const float* z_in, float* res_out, const float* r);
+// multigrid32.cu: FP64 CG preconditioned by the V-cycle evaluated in FP32 (precond == ESIMP_PRECOND_GMG_FP32)
+int pcg_solve_mg32(esimp_ctx* ctx, int* iters, double* relres);
 // multigrid.cu
 int mg_setup(esimp_ctx* ctx);          // build / refresh the hierarchy for the current E and mask
 void mg_free(esimp_ctx* ctx);
@@ -263,6 +270,8 @@ int comm_unique_id(void* id128, std::string& err);
 int comm_init(esimp_ctx* ctx, int rank, int nranks, const void* id128);
 void comm_destroy(esimp_ctx* ctx);
 int comm_allreduce(esimp_ctx* ctx, double* d_buf, long long n, bool is_max);
+int comm_allreduce_f32(esimp_ctx* ctx, float* d_buf, long long n);
+int comm_halo_nodes_lv_f32(esimp_ctx* ctx, const GridDev& g, int own_p0, int own_p1, bool has_left, bool has_right, float* v);
 int comm_halo_nodes(esimp_ctx* ctx, double* d_vec);            // one-plane u halo, both directions
 int comm_halo_cells(esimp_ctx* ctx, double* d_arr);            // halo_e-layer cell halo, both directions
 

@@ -26,6 +26,7 @@
 // ---------------------------------------------------------------------------- constants
 __constant__ double c_K0[24 * 24];  // dense unit-modulus element matrix, local dof 3a+c
 __constant__ double c_B[8][3][3];   // mode-space blocks per parity class
+__constant__ float c_Bf[8][3][3];   // the same in single precision (FP32 multigrid cycle, multigrid32.cu)
 __constant__ double c_kdiag[3];     // K0[3a+c,3a+c] (same for every node a of a cuboid)
 static const esimp_ctx* g_const_owner = nullptr;
 
@@ -171,6 +172,11 @@ int hex8_upload_constants(esimp_ctx* ctx) {
     if (g_const_owner != ctx) {
         ESIMP_CUDA(cudaMemcpyToSymbolAsync(c_K0, ctx->K0, sizeof(ctx->K0), 0, cudaMemcpyHostToDevice, ctx->stream));
         ESIMP_CUDA(cudaMemcpyToSymbolAsync(c_B, ctx->B, sizeof(ctx->B), 0, cudaMemcpyHostToDevice, ctx->stream));
+        static float Bf[8][3][3];  // static: the asynchronous copy reads it after this function returns
+        for (int q = 0; q < 8; ++q)
+            for (int c = 0; c < 3; ++c)
+                for (int d = 0; d < 3; ++d) Bf[q][c][d] = (float)ctx->B[q][c][d];
+        ESIMP_CUDA(cudaMemcpyToSymbolAsync(c_Bf, Bf, sizeof(Bf), 0, cudaMemcpyHostToDevice, ctx->stream));
         ESIMP_CUDA(cudaMemcpyToSymbolAsync(c_kdiag, ctx->kdiag, sizeof(ctx->kdiag), 0, cudaMemcpyHostToDevice, ctx->stream));
         g_const_owner = ctx;
     }
@@ -180,38 +186,51 @@ int hex8_upload_constants(esimp_ctx* ctx) {
 // ---------------------------------------------------------------------------- butterflies
 // forward 2-D transform of the 4 corner values of a (y,z) cell face:
 // F[by + 2 bz] = sum_{sy,sz} sy^by sz^bz u(sy,sz);  uYZ: first index = y offset, second = z offset
-__device__ __forceinline__ void fwd2d(double u00, double u10, double u01, double u11, double (&F)[4]) {
-    double a0 = u10 + u00, a1 = u10 - u00, b0 = u11 + u01, b1 = u11 - u01;
+template <typename T>
+__device__ __forceinline__ void fwd2d(T u00, T u10, T u01, T u11, T (&F)[4]) {
+    T a0 = u10 + u00, a1 = u10 - u00, b0 = u11 + u01, b1 = u11 - u01;
     F[0] = b0 + a0;
     F[1] = b1 + a1;
     F[2] = b0 - a0;
     F[3] = b1 - a1;
 }
 // inverse: y(sy,sz) = sum_b sy^by sz^bz A[b]
-__device__ __forceinline__ void inv2d(const double (&A)[4], double& y00, double& y10, double& y01, double& y11) {
-    double pm0 = A[0] - A[2], pm1 = A[1] - A[3], pp0 = A[0] + A[2], pp1 = A[1] + A[3];
+template <typename T>
+__device__ __forceinline__ void inv2d(const T (&A)[4], T& y00, T& y10, T& y01, T& y11) {
+    T pm0 = A[0] - A[2], pm1 = A[1] - A[3], pp0 = A[0] + A[2], pp1 = A[1] + A[3];
     y00 = pm0 - pm1;
     y10 = pm0 + pm1;
     y01 = pp0 - pp1;
     y11 = pp0 + pp1;
 }
 
+template <typename T>
+__device__ __forceinline__ T mode_block(int q, int c, int d);
+template <>
+__device__ __forceinline__ double mode_block<double>(int q, int c, int d) {
+    return c_B[q][c][d];
+}
+template <>
+__device__ __forceinline__ float mode_block<float>(int q, int c, int d) {
+    return c_Bf[q][c][d];
+}
 // w = K~ v for one cell; v, w indexed [c][m], m = bx + 2 (by + 2 bz)
-__device__ __forceinline__ void apply_blocks(const double (&v)[3][8], double (&w)[3][8]) {
+template <typename T>
+__device__ __forceinline__ void apply_blocks(const T (&v)[3][8], T (&w)[3][8]) {
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            double acc = 0.0;
+            T acc = T(0);
             bool first = true;
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 if (pat(q, c, d)) {
                     if (first) {
-                        acc = c_B[q][c][d] * v[d][q ^ (1 << d)];
+                        acc = mode_block<T>(q, c, d) * v[d][q ^ (1 << d)];
                         first = false;
                     } else {
-                        acc = fma(c_B[q][c][d], v[d][q ^ (1 << d)], acc);
+                        acc = fma(mode_block<T>(q, c, d), v[d][q ^ (1 << d)], acc);
                     }
                 }
             }
@@ -270,12 +289,12 @@ __global__ void __launch_bounds__(128) k_matvec_dense_atomic(GridDev g, int le0,
 //   perimeter cells are computed twice: deterministic, no zero-fill, ~(1-1/TY)(1-1/TZ) efficient.
 // ATOMIC=true : tiles do not overlap; perimeter nodes are combined with atomicAdd into a y whose
 //   perimeter rows/columns were zeroed first (ncu r1: 2x slower than owner tiles on B200).
-template <int TY, int TZ, int NF = 0>
+template <typename T, int TY, int TZ, int NF = 0>
 struct FusedSmem {
-    double in[4][3][TY + 1][TZ + 1];      // u of a node plane: 4-deep cp.async ring
-    double E[4][TY][TZ];                  // modulus of the cell layer consumed together with that plane
-    double out[2][3][3][TY + 1][TZ + 1];  // corner contributions c01, c10, c11 at [ty+1][tz+1]; borders stay 0
-    double fz[NF > 0 ? NF : 1][3][TY][TZ];  // fused-update operands (r | r, Dinv, d) of the plane the next flush completes;
+    T in[4][3][TY + 1][TZ + 1];      // u of a node plane: 4-deep cp.async ring
+    T E[4][TY][TZ];                  // modulus of the cell layer consumed together with that plane
+    T out[2][3][3][TY + 1][TZ + 1];  // corner contributions c01, c10, c11 at [ty+1][tz+1]; borders stay 0
+    T fz[NF > 0 ? NF : 1][3][TY][TZ];  // fused-update operands (r | r, Dinv, d) of the plane the next flush completes;
                                             // every thread only touches its own slot, so one buffer and no barrier suffice
 };
 
@@ -285,6 +304,14 @@ __device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc, bool
     int sz = valid ? 8 : 0;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc, bool valid) {
+    unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 4 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+// one scalar of the kernel's arithmetic type
+__device__ __forceinline__ void cp_async_scalar(double* smem_dst, const double* gsrc, bool valid) { cp_async8(smem_dst, gsrc, valid); }
+__device__ __forceinline__ void cp_async_scalar(float* smem_dst, const float* gsrc, bool valid) { cp_async4(smem_dst, gsrc, valid); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -299,22 +326,26 @@ __device__ __forceinline__ void cp_async_wait() {
 // r, Dinv, d of the plane are prefetched into registers at the start of the step (before the FP64 work), so
 // their latency is covered; the operator is FP64-bound, the extra bytes ride for free.
 enum { FUSE_PLAIN = 0, FUSE_DOT = 1, FUSE_SMOOTH = 2, FUSE_RESID = 3, FUSE_SMOOTH_DOT = 4 };  // 4: FUSE_SMOOTH and <r, y>
-struct FuseArgs {
-    const double* r = nullptr;
-    const double* dinv = nullptr;
-    double* d = nullptr;
-    double c1 = 0.0, c2 = 0.0;
+template <typename T>
+struct FuseArgsT {
+    const T* r = nullptr;
+    const T* dinv = nullptr;
+    T* d = nullptr;
+    T c1 = T(0), c2 = T(0);
 };
-template <int TY, int TZ, bool ATOMIC, int MINB, int MODE>
+using FuseArgs = FuseArgsT<double>;
+// T = double: the operator of the FP64 solve.  T = float: the same kernel for the single-precision multigrid cycle
+// (multigrid32.cu); the fused dot products always accumulate in double.
+template <typename T, int TY, int TZ, bool ATOMIC, int MINB, int MODE>
 __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le0, int le1, int ps0, int ps1, int chunk,
-                                                               const double* __restrict__ E, const double* __restrict__ u,
-                                                               double* __restrict__ y, double* partial, unsigned int* ticket,
-                                                               RedOut<1> dot_out, FuseArgs fa) {
+                                                               const T* __restrict__ E, const T* __restrict__ u,
+                                                               T* __restrict__ y, double* partial, unsigned int* ticket,
+                                                               RedOut<1> dot_out, FuseArgsT<T> fa) {
     constexpr bool DOT = MODE == FUSE_DOT || MODE == FUSE_SMOOTH_DOT;
     constexpr bool SMOOTH = MODE == FUSE_SMOOTH || MODE == FUSE_SMOOTH_DOT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NF = SMOOTH ? 3 : (MODE == FUSE_RESID ? 1 : 0);
-    FusedSmem<TY, TZ, NF>& sm = *reinterpret_cast<FusedSmem<TY, TZ, NF>*>(smem_raw);
+    FusedSmem<T, TY, TZ, NF>& sm = *reinterpret_cast<FusedSmem<T, TY, TZ, NF>*>(smem_raw);
     const int tid = threadIdx.x;
     const int tz = tid % TZ, ty = tid / TZ;
     constexpr int SY = ATOMIC ? TY : TY - 1, SZ = ATOMIC ? TZ : TZ - 1;
@@ -338,16 +369,16 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
     const long long plane = g.plane, plane3 = 3 * g.plane;
 
     // running pointers (strength-reduced addressing: one add per plane)
-    const double* pu = u + (long long)pl0 * plane3 + (node_ok ? (long long)ey * (g.nz + 1) + ez : 0);
-    const double* ph = u + (long long)pl0 * plane3 + (halo_ok ? (long long)hy * (g.nz + 1) + hz : 0);
-    const double* pE = E + (long long)Lstart * g.eplane + (cell_ok ? (long long)ey * g.nz + ez : 0);
-    double* py = y + (long long)pl0 * plane3 + (node_ok ? (long long)ey * (g.nz + 1) + ez : 0);
-    double* pyh = y + (long long)pl0 * plane3 + (halo_ok ? (long long)hy * (g.nz + 1) + hz : 0);
+    const T* pu = u + (long long)pl0 * plane3 + (node_ok ? (long long)ey * (g.nz + 1) + ez : 0);
+    const T* ph = u + (long long)pl0 * plane3 + (halo_ok ? (long long)hy * (g.nz + 1) + hz : 0);
+    const T* pE = E + (long long)Lstart * g.eplane + (cell_ok ? (long long)ey * g.nz + ez : 0);
+    T* py = y + (long long)pl0 * plane3 + (node_ok ? (long long)ey * (g.nz + 1) + ez : 0);
+    T* pyh = y + (long long)pl0 * plane3 + (halo_ok ? (long long)hy * (g.nz + 1) + hz : 0);
     const bool own_store = node_ok && ty >= 1 && tz >= 1;
     long long foff = (long long)pl0 * plane3 + (node_ok ? (long long)ey * (g.nz + 1) + ez : 0);  // same offset as py
 
     // zero the output tiles once (their borders are never written again)
-    for (int i = tid; i < 2 * 9 * (TY + 1) * (TZ + 1); i += TY * TZ) (&sm.out[0][0][0][0][0])[i] = 0.0;
+    for (int i = tid; i < 2 * 9 * (TY + 1) * (TZ + 1); i += TY * TZ) (&sm.out[0][0][0][0][0])[i] = T(0);
 
     // issue the asynchronous copies of plane pl0+k (and of the modulus of layer Lstart+k-1, which is
     // consumed in the same step) into ring slot k&3; always commits one group so that wait_group counts
@@ -355,13 +386,13 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
         if (k <= nsteps) {
             const int buf = k & 3;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) cp_async8(&sm.in[buf][c][ty][tz], pu + c * plane, node_ok);
+            for (int c = 0; c < 3; ++c) cp_async_scalar(&sm.in[buf][c][ty][tz], pu + c * plane, node_ok);
             if (has_halo) {
 #pragma unroll
-                for (int c = 0; c < 3; ++c) cp_async8(&sm.in[buf][c][hj][hk], ph + c * plane, halo_ok);
+                for (int c = 0; c < 3; ++c) cp_async_scalar(&sm.in[buf][c][hj][hk], ph + c * plane, halo_ok);
             }
             if (k >= 1) {
-                cp_async8(&sm.E[buf][ty][tz], pE, cell_ok);
+                cp_async_scalar(&sm.E[buf][ty][tz], pE, cell_ok);
                 pE += g.eplane;
             }
             pu += plane3;
@@ -369,42 +400,42 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
         }
         cp_async_commit();
     };
-    auto face_modes = [&](int buf, double (&F)[3][4]) {
+    auto face_modes = [&](int buf, T (&F)[3][4]) {
 #pragma unroll
         for (int c = 0; c < 3; ++c)
             fwd2d(sm.in[buf][c][ty][tz], sm.in[buf][c][ty + 1][tz], sm.in[buf][c][ty][tz + 1], sm.in[buf][c][ty + 1][tz + 1], F[c]);
     };
-    auto put_corners = [&](int buf, int c, double y01, double y10, double y11) {
+    auto put_corners = [&](int buf, int c, T y01, T y10, T y11) {
         sm.out[buf][0][c][ty + 1][tz + 1] = y01;  // -> node (ty, tz+1)
         sm.out[buf][1][c][ty + 1][tz + 1] = y10;  // -> node (ty+1, tz)
         sm.out[buf][2][c][ty + 1][tz + 1] = y11;  // -> node (ty+1, tz+1)
     };
     // combine the corner contributions of the plane py points at, write the node totals, advance py
-    auto flush_plane = [&](int buf, int ring, bool store, const double (&c00)[3]) {
+    auto flush_plane = [&](int buf, int ring, bool store, const T (&c00)[3]) {
         if (store) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                double s = c00[c] + sm.out[buf][0][c][ty + 1][tz] + sm.out[buf][1][c][ty][tz + 1] + sm.out[buf][2][c][ty][tz];
+                T s = c00[c] + sm.out[buf][0][c][ty + 1][tz] + sm.out[buf][1][c][ty][tz + 1] + sm.out[buf][2][c][ty][tz];
                 if (own_store) {
                     if (SMOOTH) {
-                        const double rv = sm.fz[0][c][ty][tz];
-                        const double v = fma(fa.c1, sm.fz[2 % NF][c][ty][tz], fa.c2 * sm.fz[1 % NF][c][ty][tz] * (rv - s));
+                        const T rv = sm.fz[0][c][ty][tz];
+                        const T v = fma(fa.c1, sm.fz[2 % NF][c][ty][tz], fa.c2 * sm.fz[1 % NF][c][ty][tz] * (rv - s));
                         (fa.d + foff)[c * plane] = v;
-                        const double znew = sm.in[ring][c][ty][tz] + v;  // the input plane is still in its ring slot
+                        const T znew = sm.in[ring][c][ty][tz] + v;  // the input plane is still in its ring slot
                         py[c * plane] = znew;
-                        if (MODE == FUSE_SMOOTH_DOT) pq[0] = fma(rv, znew, pq[0]);  // <r, z>: the PCG scalar of the next iteration
+                        if (MODE == FUSE_SMOOTH_DOT) pq[0] = fma((double)rv, (double)znew, pq[0]);  // <r, z>: the PCG scalar of the next iteration
                     } else if (MODE == FUSE_RESID) {
                         py[c * plane] = sm.fz[0][c][ty][tz] - s;
                     } else {
                         py[c * plane] = s;
                     }
-                    if (MODE == FUSE_DOT) pq[0] = fma(s, sm.in[ring][c][ty][tz], pq[0]);
+                    if (MODE == FUSE_DOT) pq[0] = fma((double)s, (double)sm.in[ring][c][ty][tz], pq[0]);
                 } else if (ATOMIC && node_ok) {
                     atomicAdd(&py[c * plane], s);
                 }
                 if (ATOMIC && halo_ok) {
                     // top row (hj == TY): cells (TY-1, hk) and (TY-1, hk-1); right column: (hj, TZ-1), (hj-1, TZ-1)
-                    double h = (hj == TY) ? ((hk < TZ ? sm.out[buf][1][c][TY][hk + 1] : 0.0) + sm.out[buf][2][c][TY][hk])
+                    T h = (hj == TY) ? ((hk < TZ ? sm.out[buf][1][c][TY][hk + 1] : T(0)) + sm.out[buf][2][c][TY][hk])
                                           : (sm.out[buf][0][c][hj + 1][TZ] + sm.out[buf][2][c][hj][TZ]);
                     atomicAdd(&pyh[c * plane], h);
                 }
@@ -420,10 +451,10 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
         if (MODE >= FUSE_SMOOTH && store && own_store) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                cp_async8(&sm.fz[0][c][ty][tz], fa.r + foff + c * plane, true);
+                cp_async_scalar(&sm.fz[0][c][ty][tz], fa.r + foff + c * plane, true);
                 if (SMOOTH) {
-                    cp_async8(&sm.fz[1 % NF][c][ty][tz], fa.dinv + foff + c * plane, true);
-                    cp_async8(&sm.fz[2 % NF][c][ty][tz], fa.d + foff + c * plane, fa.c1 != 0.0);
+                    cp_async_scalar(&sm.fz[1 % NF][c][ty][tz], fa.dinv + foff + c * plane, true);
+                    cp_async_scalar(&sm.fz[2 % NF][c][ty][tz], fa.d + foff + c * plane, fa.c1 != T(0));
                 }
             }
         }
@@ -435,12 +466,12 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
     issue_plane(2);
     cp_async_wait<1>();
     __syncthreads();
-    double Fp[3][4], Gpp[3][4];
+    T Fp[3][4], Gpp[3][4];
     face_modes(0, Fp);
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) Gpp[c][b] = 0.0;
+        for (int b = 0; b < 4; ++b) Gpp[c][b] = T(0);
     issue_plane(3);
 
     int lp = pl0;  // plane the current step completes
@@ -449,24 +480,24 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
     auto step = [&](auto bufc, int it) {
         constexpr int BUF = decltype(bufc)::value;
         const int ring = (it + 1) & 3;  // slot of plane pl0+it+1 and of this layer's modulus
-        const double Ee = sm.E[ring][ty][tz];
-        double Fn[3][4];
+        const T Ee = sm.E[ring][ty][tz];
+        T Fn[3][4];
         face_modes(ring, Fn);
         // x butterfly with the modulus folded in: v0 = E (Fn + Fp), v1 = E (Fn - Fp)
-        double v[3][8], w[3][8];
+        T v[3][8], w[3][8];
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                double ep = Ee * Fp[c][b];
+                T ep = Ee * Fp[c][b];
                 v[c][2 * b] = fma(Ee, Fn[c][b], ep);
                 v[c][2 * b + 1] = fma(Ee, Fn[c][b], -ep);
             }
         apply_blocks(v, w);
-        double c00[3];
+        T c00[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            double A[4];
+            T A[4];
 #pragma unroll
             // b = 0: w[c][0] is the translation mode, structurally zero (written out so that no 0 -+ x is issued)
             A[0] = Gpp[c][0] - w[c][1];
@@ -478,7 +509,7 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
                 Gpp[c][b] = w[c][2 * b] + w[c][2 * b + 1];
                 Fp[c][b] = Fn[c][b];
             }
-            double y10, y01, y11;
+            T y10, y01, y11;
             inv2d(A, c00[c], y10, y01, y11);
             put_corners(BUF, c, y01, y10, y11);
         }
@@ -501,10 +532,10 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
     if (it < nsteps) step(std::integral_constant<int, 0>{}, it);
     // ---- epilogue: the last plane only receives Gp of the last cell
     {
-        double c00[3];
+        T c00[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            double y10, y01, y11;
+            T y10, y01, y11;
             inv2d(Gpp[c], c00[c], y10, y01, y11);
             put_corners(nsteps & 1, c, y01, y10, y11);
         }
@@ -531,8 +562,10 @@ __global__ void k_zero_perimeter(GridDev g, int ps0, int ps1, double* __restrict
     }
 }
 
-template <int TY, int TZ, bool ATOMIC, int MINB, int MODE>
-static int launch_fused_t(esimp_ctx* ctx, const OpView& vw, const double* d_in, double* d_out, int dot_slot, const FuseArgs& fa = FuseArgs()) {
+// vw supplies the geometry; E_t is the modulus array in the kernel's arithmetic type (vw.E for T = double)
+template <typename T, int TY, int TZ, bool ATOMIC, int MINB, int MODE>
+static int launch_fused_tt(esimp_ctx* ctx, const OpView& vw, const T* E_t, bool fine, const T* d_in, T* d_out, int dot_slot,
+                           const FuseArgsT<T>& fa) {
     constexpr bool DOT = MODE == FUSE_DOT || MODE == FUSE_SMOOTH_DOT;
     const GridDev& g = vw.g;
     constexpr int SY = ATOMIC ? TY : TY - 1, SZ = ATOMIC ? TZ : TZ - 1;
@@ -545,15 +578,15 @@ static int launch_fused_t(esimp_ctx* ctx, const OpView& vw, const double* d_in, 
     while (chunk > 8 && tiles * ((nplanes + chunk - 1) / chunk) < 148LL * MINB * 6) chunk = (chunk + 1) / 2;
     if (ctx->fused_chunk > 0) chunk = ctx->fused_chunk;
     const int nchunk = (nplanes + chunk - 1) / chunk;
-    const size_t smem = sizeof(FusedSmem<TY, TZ, (MODE == FUSE_SMOOTH || MODE == FUSE_SMOOTH_DOT) ? 3 : (MODE == FUSE_RESID ? 1 : 0)>);
+    const size_t smem = sizeof(FusedSmem<T, TY, TZ, (MODE == FUSE_SMOOTH || MODE == FUSE_SMOOTH_DOT) ? 3 : (MODE == FUSE_RESID ? 1 : 0)>);
     static unsigned long long attr_devices = 0;  // the attribute is per device: one bit per device this process has used
-    auto kern = k_matvec_fused<TY, TZ, ATOMIC, MINB, MODE>;
+    auto kern = k_matvec_fused<T, TY, TZ, ATOMIC, MINB, MODE>;
     const unsigned long long dev_bit = 1ull << (ctx->device & 63);
     if (!(attr_devices & dev_bit)) {
         ESIMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_devices |= dev_bit;
     }
-    if (ATOMIC) {
+    if constexpr (ATOMIC && std::is_same<T, double>::value) {
         k_zero_perimeter<TY, TZ><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(g, vw.own_p0, vw.own_p1, d_out);
         ctx->launches++;
     }
@@ -567,15 +600,21 @@ static int launch_fused_t(esimp_ctx* ctx, const OpView& vw, const double* d_in, 
     RedOut<1> dot_out{{ctx->d_scal + (DOT ? dot_slot : 0)}};
     // only fine-grid applies are timed (multigrid levels reuse this kernel on coarser grids)
     // every fine-grid launch is timed; tag 0 = plain / dot applies (the roofline number), 1 = fused smoother / residual modes
-    const bool timed = ctx->prof_on && vw.E == ctx->d_E && 2 * ctx->prof_n + 1 < (int)ctx->prof_ev.size();
+    const bool timed = ctx->prof_on && fine && 2 * ctx->prof_n + 1 < (int)ctx->prof_ev.size();
     if (timed) ctx->prof_tag[ctx->prof_n] = MODE <= FUSE_DOT ? 0 : 1;
     if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
-    kern<<<grid, block, smem, ctx->stream>>>(g, vw.mv_e0, vw.mv_e1, vw.own_p0, vw.own_p1, chunk, vw.E, d_in, d_out,
+    kern<<<grid, block, smem, ctx->stream>>>(g, vw.mv_e0, vw.mv_e1, vw.own_p0, vw.own_p1, chunk, E_t, d_in, d_out,
                                              ctx->d_partial_mv, ctx->d_ticket + 2, dot_out, fa);
     if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n++ + 1], ctx->stream);
     ctx->launches++;
     ESIMP_CUDA(cudaGetLastError());
     return ESIMP_OK;
+}
+
+// the FP64 operator: modulus from the view, fine grid = the context's own modulus array
+template <int TY, int TZ, bool ATOMIC, int MINB, int MODE>
+static int launch_fused_t(esimp_ctx* ctx, const OpView& vw, const double* d_in, double* d_out, int dot_slot, const FuseArgs& fa = FuseArgs()) {
+    return launch_fused_tt<double, TY, TZ, ATOMIC, MINB, MODE>(ctx, vw, vw.E, vw.E == ctx->d_E, d_in, d_out, dot_slot, fa);
 }
 
 template <int TY, int TZ, bool ATOMIC, int MINB>
@@ -627,6 +666,24 @@ int hex8_resid_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double
     FuseArgs fa;
     fa.r = r;
     return launch_fused_t<16, 16, false, 2, FUSE_RESID>(ctx, vw, z_in, res_out, -1, fa);
+}
+// ---- single-precision instances for the FP32 multigrid cycle (multigrid32.cu): same kernel, T = float
+int hex8_smooth_view_f32(esimp_ctx* ctx, const OpView& vw, const float* E, const float* z_in, float* z_out, const float* r,
+                         const float* dinv, float* d, float c1, float c2) {
+    ESIMP_TRY(hex8_upload_constants(ctx));
+    FuseArgsT<float> fa;
+    fa.r = r;
+    fa.dinv = dinv;
+    fa.d = d;
+    fa.c1 = c1;
+    fa.c2 = c2;
+    return launch_fused_tt<float, 16, 16, false, 2, FUSE_SMOOTH>(ctx, vw, E, vw.g.nx == ctx->g.nx, z_in, z_out, -1, fa);
+}
+int hex8_resid_view_f32(esimp_ctx* ctx, const OpView& vw, const float* E, const float* z_in, float* res_out, const float* r) {
+    ESIMP_TRY(hex8_upload_constants(ctx));
+    FuseArgsT<float> fa;
+    fa.r = r;
+    return launch_fused_tt<float, 16, 16, false, 2, FUSE_RESID>(ctx, vw, E, vw.g.nx == ctx->g.nx, z_in, res_out, -1, fa);
 }
 OpView fine_view(const esimp_ctx* ctx) {
     OpView v;

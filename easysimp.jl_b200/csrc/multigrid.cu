@@ -246,6 +246,8 @@ void mg_free(esimp_ctx* ctx) {
         cudaFree(L.d_z2);
         cudaFree(L.d_d);
         cudaFree(L.d_pi);
+        float* f32[] = {L.f_E, L.f_dinv, L.f_r, L.f_z, L.f_z2, L.f_d, L.f_q};
+        for (float* p : f32) cudaFree(p);
         if (l > 0) {
             cudaFree(L.d_E);
             cudaFree(L.d_mask);

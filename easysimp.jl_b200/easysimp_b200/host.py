@@ -444,7 +444,9 @@ class OptimizationParameters:
     pcg_maxit: int = 200000
     pcg_check_every: int = 25
     matvec_variant: int = 0
-    preconditioner: str = "auto"  # "jacobi" | "gmg" | "auto" (gmg on generate_grid grids, jacobi on imported meshes)
+    # "jacobi" | "gmg" | "auto" (gmg on generate_grid grids, jacobi on imported meshes) | "gmg_fp32" (opt-in: the V-cycle
+    # evaluated in single precision inside the FP64 CG, csrc/multigrid32.cu)
+    preconditioner: str = "auto"
 
 
 @dataclass
@@ -471,7 +473,8 @@ def _configure(ctx, grid, params: OptimizationParameters, fcache: FilterCache):
                    move_limit=params.move_limit, damping=params.damping, filter_radius=fcache.filter_radius, filter_type=ftype,
                    pcg_rtol=params.pcg_rtol, pcg_maxit=params.pcg_maxit, pcg_check_every=params.pcg_check_every,
                    matvec_variant=params.matvec_variant, warm_start=1,
-                   precond=int(params.preconditioner == "gmg" or (params.preconditioner == "auto" and fcache.structured)))
+                   precond=2 if params.preconditioner == "gmg_fp32" else
+                   int(params.preconditioner == "gmg" or (params.preconditioner == "auto" and fcache.structured)))
     if fcache.structured:
         ctx.filter_build_structured()
     else:

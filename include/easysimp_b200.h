@@ -58,6 +58,8 @@ extern "C" {
 /* CG preconditioners */
 #define ESIMP_PRECOND_JACOBI 0 /* diagonal scaling                                                        */
 #define ESIMP_PRECOND_GMG 1    /* geometric multigrid V-cycle on structured grids (csrc/multigrid.cu)     */
+#define ESIMP_PRECOND_GMG_FP32 2 /* the same V-cycle evaluated in single precision inside the FP64 CG (csrc/multigrid32.cu);
+                                    opt-in, written for round 2 and not yet validated on a GPU                */
 
 typedef struct esimp_ctx esimp_ctx;
 
