@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/easysimp_b200.h"
+#include "grid_dev.h"
 
 #define ESIMP_CUDA(call)                                                                         \
     do {                                                                                         \
@@ -30,27 +31,6 @@
         int _s = (expr);             \
         if (_s < 0) return _s;       \
     } while (0)
-
-// geometry of the slab this rank holds (all ints fit 32 bit; flat indices are 64 bit)
-struct GridDev {
-    int nx, ny, nz;        // global element counts
-    int NPX;               // local node planes stored
-    int NEX;               // local element layers stored
-    int gp0;               // global x index of local node plane 0
-    int ge0;               // global x index of local element layer 0
-    int e2p;               // local plane of the low face of local layer le = le + e2p
-    long long plane;       // (ny+1)*(nz+1)
-    long long eplane;      // ny*nz
-    __host__ __device__ long long dof(int lp, int c, int j, int k) const {
-        return ((long long)(lp * 3 + c) * (ny + 1) + j) * (nz + 1) + k;
-    }
-    __host__ __device__ long long node(int lp, int j, int k) const {
-        return ((long long)lp * (ny + 1) + j) * (nz + 1) + k;
-    }
-    __host__ __device__ long long cell(int le, int j, int k) const {
-        return ((long long)le * ny + j) * nz + k;
-    }
-};
 
 // what the structured operator needs to know about one grid level (fine grid or a multigrid level)
 struct OpView {
@@ -291,10 +271,6 @@ __device__ __forceinline__ double warp_max(double v) {
 // Deterministic grid reduction of NV values: warp shuffle -> smem -> per-block partial ->
 // the last block to finish (ticket) folds the partials in a fixed order and writes out[i].
 // partial: [NV][gridDim.x]; all threads of all blocks must call it.
-template <int NV>
-struct RedOut {
-    double* p[NV];
-};
 template <int NV, bool IS_MAX>
 __device__ __forceinline__ void grid_reduce_idx(double (&v)[NV], double* partial, unsigned int* ticket, const RedOut<NV>& out,
                                                 unsigned int bid, unsigned int nblk);

@@ -1,0 +1,164 @@
+// selftest_kernel_host.cpp -- runs the fused hex8 operator kernel (fused_kernel.cuh, the very source nvcc compiles into
+// libeasysimp_b200.so) on the CPU: every thread of a CUDA block is a host thread, __syncthreads is a barrier,
+// cp.async copies complete at once, blocks run one after the other.  TEST INFRASTRUCTURE for the -m "not gpu"
+// suite (tests/test_kernel_emulation.py): not linked into the product library, nothing in the product calls it.
+// It checks the kernel's LOGIC (tiling, ring indexing, butterflies, store modes, float instantiation); it cannot
+// prove the absence of races that depend on the real completion order of asynchronous copies.
+#define ESIMP_HOST_EMULATION 1
+#include <algorithm>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <mutex>
+#include <thread>
+#include <type_traits>
+#include <vector>
+
+using std::fma;
+using std::max;
+using std::min;
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __shared__
+#define __align__(n)
+
+struct EmuDim3 {
+    unsigned x = 1, y = 1, z = 1;
+};
+static thread_local EmuDim3 threadIdx;
+static EmuDim3 blockIdx, blockDim, gridDim;
+alignas(16) unsigned char smem_raw[256 * 1024];  // the block's dynamic shared memory (blocks run sequentially)
+static std::barrier<>* g_barrier = nullptr;
+static std::mutex g_mutex;
+inline void __syncthreads() { g_barrier->arrive_and_wait(); }
+template <typename T>
+inline void atomicAdd(T* p, T v) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    *p += v;
+}
+
+double c_B[8][3][3];
+float c_Bf[8][3][3];
+
+#include "grid_dev.h"
+
+// the fused dot product: every thread of every block contributes its partial sum
+template <int NV, bool IS_MAX>
+inline void grid_reduce_idx(double (&v)[NV], double*, unsigned int*, const RedOut<NV>& out, unsigned int, unsigned int) {
+    std::lock_guard<std::mutex> lock(g_mutex);
+    for (int i = 0; i < NV; ++i) *out.p[i] = IS_MAX ? std::max(*out.p[i], v[i]) : *out.p[i] + v[i];
+}
+
+#include "fused_kernel.cuh"
+
+namespace {
+
+constexpr int TY = 16, TZ = 16;
+
+template <typename T, int MODE>
+void run_grid(const GridDev& g, int chunk, const T* E, const T* u, T* y, double* dot, const FuseArgsT<T>& fa) {
+    constexpr int SY = TY - 1, SZ = TZ - 1;
+    const int nty = (g.ny + 1 + SY - 1) / SY, ntz = (g.nz + 1 + SZ - 1) / SZ;
+    const int nplanes = g.NPX;
+    if (chunk <= 0) chunk = nplanes;
+    const int nchunk = (nplanes + chunk - 1) / chunk;
+    gridDim = EmuDim3{(unsigned)ntz, (unsigned)nty, (unsigned)nchunk};
+    blockDim = EmuDim3{(unsigned)(TY * TZ), 1, 1};
+    RedOut<1> out{{dot}};
+    for (int bz = 0; bz < nchunk; ++bz)
+        for (int by = 0; by < nty; ++by)
+            for (int bx = 0; bx < ntz; ++bx) {
+                blockIdx = EmuDim3{(unsigned)bx, (unsigned)by, (unsigned)bz};
+                std::barrier<> barrier(TY * TZ);
+                g_barrier = &barrier;
+                std::vector<std::thread> threads;
+                threads.reserve(TY * TZ);
+                for (int t = 0; t < TY * TZ; ++t)
+                    threads.emplace_back([&, t] {
+                        threadIdx = EmuDim3{(unsigned)t, 0, 0};
+                        k_matvec_fused<T, TY, TZ, false, 2, MODE>(g, 0, g.NEX, 0, g.NPX, chunk, E, u, y, nullptr, nullptr, out, fa);
+                    });
+                for (auto& th : threads) th.join();
+            }
+}
+
+template <typename T>
+int run_mode(int mode, const GridDev& g, int chunk, const T* E, const T* u, T* y, double* dot, const FuseArgsT<T>& fa) {
+    switch (mode) {
+        case FUSE_PLAIN: run_grid<T, FUSE_PLAIN>(g, chunk, E, u, y, dot, fa); return 0;
+        case FUSE_DOT: run_grid<T, FUSE_DOT>(g, chunk, E, u, y, dot, fa); return 0;
+        case FUSE_SMOOTH: run_grid<T, FUSE_SMOOTH>(g, chunk, E, u, y, dot, fa); return 0;
+        case FUSE_RESID: run_grid<T, FUSE_RESID>(g, chunk, E, u, y, dot, fa); return 0;
+        case FUSE_SMOOTH_DOT: run_grid<T, FUSE_SMOOTH_DOT>(g, chunk, E, u, y, dot, fa); return 0;
+    }
+    return -1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int emu_pat(int q, int c, int d) { return pat(q, c, d) ? 1 : 0; }
+
+// One launch of the fused kernel on an nx x ny x nz single-rank grid.  All vectors in the library's device layout
+// (node vectors [plane][component][y][z], cell array [layer][y][z]); `blocks` = the 8x3x3 mode-space blocks of the
+// cuboid; r / dinv / d are the smoother operands (d is updated in place), unused ones may be NULL.
+int emu_fused(int is_float, int mode, int nx, int ny, int nz, int chunk, const double* blocks, const double* E, const double* u,
+              const double* r, const double* dinv, double* d, double c1, double c2, double* y, double* dot) {
+    GridDev g;
+    g.nx = nx;
+    g.ny = ny;
+    g.nz = nz;
+    g.NPX = nx + 1;
+    g.NEX = nx;
+    g.gp0 = g.ge0 = g.e2p = 0;
+    g.plane = (long long)(ny + 1) * (nz + 1);
+    g.eplane = (long long)ny * nz;
+    const long long nd = 3 * g.NPX * g.plane, nc = (long long)g.NEX * g.eplane;
+    for (int q = 0; q < 8; ++q)
+        for (int c = 0; c < 3; ++c)
+            for (int e = 0; e < 3; ++e) {
+                c_B[q][c][e] = blocks[(q * 3 + c) * 3 + e];
+                c_Bf[q][c][e] = (float)c_B[q][c][e];
+            }
+    if (dot) *dot = 0.0;
+    double dummy = 0.0;
+    if (!is_float) {
+        FuseArgsT<double> fa;
+        fa.r = r;
+        fa.dinv = dinv;
+        fa.d = d;
+        fa.c1 = c1;
+        fa.c2 = c2;
+        return run_mode<double>(mode, g, chunk, E, u, y, dot ? dot : &dummy, fa);
+    }
+    std::vector<float> Ef(E, E + nc), uf(u, u + nd), yf(nd), rf, df, dinvf;
+    for (long long i = 0; i < nd; ++i) yf[i] = (float)y[i];
+    FuseArgsT<float> fa;
+    if (r) {
+        rf.assign(r, r + nd);
+        fa.r = rf.data();
+    }
+    if (dinv) {
+        dinvf.assign(dinv, dinv + nd);
+        fa.dinv = dinvf.data();
+    }
+    if (d) {
+        df.assign(d, d + nd);
+        fa.d = df.data();
+    }
+    fa.c1 = (float)c1;
+    fa.c2 = (float)c2;
+    int st = run_mode<float>(mode, g, chunk, Ef.data(), uf.data(), yf.data(), dot ? dot : &dummy, fa);
+    for (long long i = 0; i < nd; ++i) y[i] = yf[i];
+    if (d)
+        for (long long i = 0; i < nd; ++i) d[i] = df[i];
+    return st;
+}
+}
