@@ -59,9 +59,7 @@ inline void grid_reduce_idx(double (&v)[NV], double*, unsigned int*, const RedOu
 
 namespace {
 
-constexpr int TY = 16, TZ = 16;
-
-template <typename T, int MODE>
+template <typename T, int MODE, int TY = 16, int TZ = 16>
 void run_grid(const GridDev& g, int chunk, const T* E, const T* u, T* y, double* dot, const FuseArgsT<T>& fa) {
     constexpr int SY = TY - 1, SZ = TZ - 1;
     const int nty = (g.ny + 1 + SY - 1) / SY, ntz = (g.nz + 1 + SZ - 1) / SZ;
@@ -103,6 +101,35 @@ int run_mode(int mode, const GridDev& g, int chunk, const T* E, const T* u, T* y
 }  // namespace
 
 extern "C" {
+
+// plain operator with the other owner-computes tile shapes the library can select (ESIMP_MATVEC_FUSED_8x16 / _8x32)
+int emu_fused_tile(int ty, int tz, int nx, int ny, int nz, int chunk, const double* blocks, const double* E, const double* u, double* y) {
+    GridDev g;
+    g.nx = nx;
+    g.ny = ny;
+    g.nz = nz;
+    g.NPX = nx + 1;
+    g.NEX = nx;
+    g.gp0 = g.ge0 = g.e2p = 0;
+    g.plane = (long long)(ny + 1) * (nz + 1);
+    g.eplane = (long long)ny * nz;
+    for (int q = 0; q < 8; ++q)
+        for (int c = 0; c < 3; ++c)
+            for (int e = 0; e < 3; ++e) c_B[q][c][e] = blocks[(q * 3 + c) * 3 + e];
+    double dummy = 0.0;
+    FuseArgsT<double> fa;
+    if (ty == 8 && tz == 16) {
+        run_grid<double, FUSE_PLAIN, 8, 16>(g, chunk, E, u, y, &dummy, fa);
+    } else if (ty == 8 && tz == 32) {
+        run_grid<double, FUSE_PLAIN, 8, 32>(g, chunk, E, u, y, &dummy, fa);
+    } else if (ty == 16 && tz == 16) {
+        run_grid<double, FUSE_PLAIN, 16, 16>(g, chunk, E, u, y, &dummy, fa);
+    } else {
+        return -1;
+    }
+    return 0;
+}
+
 
 int emu_pat(int q, int c, int d) { return pat(q, c, d) ? 1 : 0; }
 

@@ -23,6 +23,7 @@ def emu():
     lib = C.CDLL(str(path))
     lib.emu_fused.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, D, D, D, D, D, D, C.c_double, C.c_double, D, D]
     lib.emu_pat.argtypes = [C.c_int] * 3
+    lib.emu_fused_tile.argtypes = [C.c_int] * 6 + [D, D, D, D]
     return lib
 
 
@@ -124,6 +125,16 @@ def test_plain_and_dot_modes_match_the_assembled_operator(emu, nel, right, chunk
     assert not np.isnan(y).any() and relmax(y, want) < 2e-13
     y2, _, dot = p.run(emu, DOT, u, chunk=chunk)
     assert np.array_equal(y, y2) and abs(dot - u @ want) < 1e-11 * abs(u @ want)
+
+
+@pytest.mark.parametrize("ty,tz", [(8, 16), (8, 32), (16, 16)])
+def test_other_tile_shapes(emu, ty, tz):
+    """the 8x16 and 8x32 owner-computes tiles (ESIMP_MATVEC_FUSED_8x16 / _8x32) on a grid that needs several tiles each way"""
+    p = Problem((4, 17, 33), (4.0, 17.0, 33.0), seed=3)
+    u = p.rng.standard_normal(p.nd)
+    y = np.full(p.nd, np.nan)
+    assert emu.emu_fused_tile(ty, tz, 4, 17, 33, 0, ptr(p.B.ravel()), ptr(p.cells_dev(p.E)), ptr(p.to_dev(u)), ptr(y)) == 0
+    assert relmax(p.from_dev(y), p.A(u)) < 2e-13
 
 
 @pytest.mark.parametrize("nel,right,chunk", GRIDS[:3])
