@@ -55,7 +55,13 @@ inline void grid_reduce_idx(double (&v)[NV], double*, unsigned int*, const RedOu
     for (int i = 0; i < NV; ++i) *out.p[i] = IS_MAX ? std::max(*out.p[i], v[i]) : *out.p[i] + v[i];
 }
 
+template <int NV, bool IS_MAX>
+inline void grid_reduce(double (&v)[NV], double* partial, unsigned int* ticket, const RedOut<NV>& out) {
+    grid_reduce_idx<NV, IS_MAX>(v, partial, ticket, out, 0u, 1u);
+}
+
 #include "fused_kernel.cuh"
+#include "mg32_kernels.cuh"
 
 namespace {
 
@@ -98,9 +104,81 @@ int run_mode(int mode, const GridDev& g, int chunk, const T* E, const T* u, T* y
     return -1;
 }
 
+GridDev level_grid(int nx, int ny, int nz) {
+    GridDev g;
+    g.nx = nx;
+    g.ny = ny;
+    g.nz = nz;
+    g.NPX = nx + 1;
+    g.NEX = nx;
+    g.gp0 = g.ge0 = g.e2p = 0;
+    g.plane = (long long)(ny + 1) * (nz + 1);
+    g.eplane = (long long)ny * nz;
+    return g;
+}
+
+// the grid-stride kernels of mg32_kernels.cuh run as ONE thread of a 1x1 grid: it strides over every element
+void single_thread() {
+    gridDim = blockDim = EmuDim3{1, 1, 1};
+    blockIdx = EmuDim3{0, 0, 0};
+    threadIdx = EmuDim3{0, 0, 0};
+}
+
 }  // namespace
 
 extern "C" {
+
+// ---- the FP32 V-cycle's vector / transfer kernels (mg32_kernels.cuh), single rank, device layouts
+void emu_k32_restrict(int fnx, int fny, int fnz, const float* resf, const uint8_t* maskc, float* rc) {
+    single_thread();
+    GridDev gf = level_grid(fnx, fny, fnz), gc = level_grid(fnx / 2, fny / 2, fnz / 2);
+    k32_restrict(gf, gc, 0, gc.NPX, resf, maskc, rc);
+}
+void emu_k32_prolong_add(int fnx, int fny, int fnz, const float* zc, const uint8_t* maskf, float* zf) {
+    single_thread();
+    GridDev gf = level_grid(fnx, fny, fnz), gc = level_grid(fnx / 2, fny / 2, fnz / 2);
+    k32_prolong_add(gf, gc, 0, gf.NPX, zc, maskf, zf);
+}
+void emu_k32_cheb_first(long long n, const float* r, const float* dinv, float inv_theta, float* d, float* z) {
+    single_thread();
+    k32_cheb_first(r, dinv, inv_theta, d, z, 0, n);
+}
+void emu_k32_enter(long long n, const double* r, double inv_s, const float* dinv, float inv_theta, float* r32, float* d, float* z) {
+    single_thread();
+    k32_enter(r, inv_s, dinv, inv_theta, r32, d, z, 0, n);
+}
+void emu_k32_fixup(const long long* fixed, long long n, float m, const float* in, float* out) {
+    single_thread();
+    k32_fixup(fixed, n, m, in, out);
+}
+void emu_k32_convert(long long n, const double* src, float* dst) {
+    single_thread();
+    k32_convert(src, dst, n);
+}
+double emu_k32_dot_rz(long long n, const double* r, const float* z, double s) {
+    single_thread();
+    double acc = 0.0;
+    RedOut<1> out{{&acc}};
+    k32_dot_rz(r, z, s, 0, n, nullptr, nullptr, out);
+    return acc;
+}
+double emu_k32_update(long long n, const double* q, double* r, double rz, double pq) {
+    single_thread();
+    double acc = 0.0;
+    RedOut<1> out{{&acc}};
+    k32_update(q, r, 0, n, &rz, &pq, nullptr, nullptr, out);
+    return acc;
+}
+void emu_k32_init(long long n, const double* f, const double* q, double* r, double* rr_ff) {
+    single_thread();
+    rr_ff[0] = rr_ff[1] = 0.0;
+    RedOut<2> out{{rr_ff, rr_ff + 1}};
+    k32_init(f, q, r, 0, n, nullptr, nullptr, out);
+}
+void emu_k32_direction(long long n, const float* z, double s, double* p, double* x, double rz_new, double rz_old, double pq, int mode) {
+    single_thread();
+    k32_direction(z, s, p, x, 0, n, &rz_new, &rz_old, &pq, mode);
+}
 
 // plain operator with the other owner-computes tile shapes the library can select (ESIMP_MATVEC_FUSED_8x16 / _8x32)
 int emu_fused_tile(int ty, int tz, int nx, int ny, int nz, int chunk, const double* blocks, const double* E, const double* u, double* y) {
