@@ -211,6 +211,53 @@ int emu_fused_tile(int ty, int tz, int nx, int ny, int nz, int chunk, const doub
 
 int emu_pat(int q, int c, int d) { return pat(q, c, d) ? 1 : 0; }
 
+// plain FP64 operator on ONE x-slab of a partitioned grid: the caller passes the slab geometry esimp_set_grid_structured
+// builds (gp0, NPX, ge0, NEX, owned planes [ps0, ps1), visited layers [le0, le1)) and the slab's local arrays
+int emu_fused_slab(int nx, int ny, int nz, int gp0, int npx, int ge0, int nex, int ps0, int ps1, int le0, int le1, int chunk,
+                   const double* blocks, const double* E_loc, const double* u_loc, double* y_loc) {
+    GridDev g;
+    g.nx = nx;
+    g.ny = ny;
+    g.nz = nz;
+    g.NPX = npx;
+    g.NEX = nex;
+    g.gp0 = gp0;
+    g.ge0 = ge0;
+    g.e2p = ge0 - gp0;
+    g.plane = (long long)(ny + 1) * (nz + 1);
+    g.eplane = (long long)ny * nz;
+    for (int q = 0; q < 8; ++q)
+        for (int c = 0; c < 3; ++c)
+            for (int e = 0; e < 3; ++e) c_B[q][c][e] = blocks[(q * 3 + c) * 3 + e];
+    constexpr int TY = 16, TZ = 16, SY = TY - 1, SZ = TZ - 1;
+    const int nty = (ny + 1 + SY - 1) / SY, ntz = (nz + 1 + SZ - 1) / SZ;
+    const int nplanes = ps1 - ps0;
+    if (chunk <= 0) chunk = nplanes;
+    const int nchunk = (nplanes + chunk - 1) / chunk;
+    gridDim = EmuDim3{(unsigned)ntz, (unsigned)nty, (unsigned)nchunk};
+    blockDim = EmuDim3{(unsigned)(TY * TZ), 1, 1};
+    double dummy = 0.0;
+    RedOut<1> out{{&dummy}};
+    FuseArgsT<double> fa;
+    for (int bz = 0; bz < nchunk; ++bz)
+        for (int by = 0; by < nty; ++by)
+            for (int bx = 0; bx < ntz; ++bx) {
+                blockIdx = EmuDim3{(unsigned)bx, (unsigned)by, (unsigned)bz};
+                std::barrier<> barrier(TY * TZ);
+                g_barrier = &barrier;
+                std::vector<std::thread> threads;
+                threads.reserve(TY * TZ);
+                for (int t = 0; t < TY * TZ; ++t)
+                    threads.emplace_back([&, t] {
+                        threadIdx = EmuDim3{(unsigned)t, 0, 0};
+                        k_matvec_fused<double, TY, TZ, false, 2, FUSE_PLAIN>(g, le0, le1, ps0, ps1, chunk, E_loc, u_loc, y_loc, nullptr, nullptr,
+                                                                             out, fa);
+                    });
+                for (auto& th : threads) th.join();
+            }
+    return 0;
+}
+
 // One launch of the fused kernel on an nx x ny x nz single-rank grid.  All vectors in the library's device layout
 // (node vectors [plane][component][y][z], cell array [layer][y][z]); `blocks` = the 8x3x3 mode-space blocks of the
 // cuboid; r / dinv / d are the smoother operands (d is updated in place), unused ones may be NULL.

@@ -24,6 +24,7 @@ def emu():
     lib.emu_fused.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, D, D, D, D, D, D, C.c_double, C.c_double, D, D]
     lib.emu_pat.argtypes = [C.c_int] * 3
     lib.emu_fused_tile.argtypes = [C.c_int] * 6 + [D, D, D, D]
+    lib.emu_fused_slab.argtypes = [C.c_int] * 12 + [D, D, D, D]
     return lib
 
 
@@ -173,3 +174,33 @@ def test_single_precision_instantiation(emu, nel, right, chunk):
     assert relmax(y, z + v) < 2e-5 and relmax(dnew, v) < 2e-5
     y, _, _ = p.run(emu, RESID, z, is_float=True, chunk=chunk, r=r)
     assert relmax(y, r - Az) < 2e-5
+
+
+@pytest.mark.parametrize("nranks,halo_e,chunk", [(2, 1, 0), (3, 2, 0), (4, 1, 2)])
+def test_x_slab_partition_reproduces_the_global_operator(emu, nranks, halo_e, chunk):
+    """every rank runs the kernel on its slab (owned planes + one ghost plane per interior side, the redundant left
+    interface layer, `halo_e` ghost cell layers: easysimp_b200/partition.py = esimp_set_grid_structured); the owned
+    planes of all ranks together are the global y, and nothing outside them is written"""
+    import easysimp_b200.partition as part
+
+    p = Problem((13, 6, 5), (13.0, 6.0, 5.0), seed=4)
+    nx, ny, nz = p.nel
+    u = p.rng.standard_normal(p.nd)
+    want = p.to_dev(p.A(u)).reshape(nx + 1, -1)
+    udev, Edev = p.to_dev(u).reshape(nx + 1, -1), p.cells_dev(p.E).reshape(nx, -1)
+    covered = np.zeros(nx + 1, dtype=int)
+    for r in range(nranks):
+        sl = part.slab_partition(nx, r, nranks, halo_e)
+        u_loc = np.ascontiguousarray(udev[sl.gp0:sl.gp0 + sl.npx]).ravel()
+        E_loc = np.ascontiguousarray(Edev[sl.ge0:sl.ge0 + sl.nex]).ravel()
+        y_loc = np.full(u_loc.size, np.nan)
+        assert emu.emu_fused_slab(nx, ny, nz, sl.gp0, sl.npx, sl.ge0, sl.nex, sl.own_p0, sl.own_p1, sl.mv_e0, sl.mv_e1, chunk,
+                                  ptr(p.B.ravel()), ptr(E_loc), ptr(u_loc), ptr(y_loc)) == 0
+        y_loc = y_loc.reshape(sl.npx, -1)
+        own = slice(sl.own_p0, sl.own_p1)
+        assert relmax(y_loc[own], want[sl.gp0 + sl.own_p0:sl.gp0 + sl.own_p1]) < 2e-13
+        ghost = np.ones(sl.npx, dtype=bool)
+        ghost[own] = False
+        assert np.isnan(y_loc[ghost]).all()  # ghost planes are never stored: only u moves between ranks
+        covered[sl.gp0 + sl.own_p0:sl.gp0 + sl.own_p1] += 1
+    assert (covered == 1).all()
