@@ -17,6 +17,7 @@
 // x-direction butterfly of the output is shared the same way, so a cell costs 162 FP64 issue
 // slots instead of 600 and each u value is read from HBM once.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <type_traits>
@@ -332,12 +333,17 @@ int hex8_smooth_view_f32(esimp_ctx* ctx, const OpView& vw, const float* E, const
     fa.d = d;
     fa.c1 = c1;
     fa.c2 = c2;
+    // tuning knob for round 2: 3 CTAs of 256 threads per SM (<= 85 registers) instead of 2
+    static const bool three = getenv("ESIMP_F32_CTAS") && atoi(getenv("ESIMP_F32_CTAS")) == 3;
+    if (three) return launch_fused_tt<float, 16, 16, false, 3, FUSE_SMOOTH>(ctx, vw, E, vw.g.nx == ctx->g.nx, z_in, z_out, -1, fa);
     return launch_fused_tt<float, 16, 16, false, 2, FUSE_SMOOTH>(ctx, vw, E, vw.g.nx == ctx->g.nx, z_in, z_out, -1, fa);
 }
 int hex8_resid_view_f32(esimp_ctx* ctx, const OpView& vw, const float* E, const float* z_in, float* res_out, const float* r) {
     ESIMP_TRY(hex8_upload_constants(ctx));
     FuseArgsT<float> fa;
     fa.r = r;
+    static const bool three = getenv("ESIMP_F32_CTAS") && atoi(getenv("ESIMP_F32_CTAS")) == 3;
+    if (three) return launch_fused_tt<float, 16, 16, false, 3, FUSE_RESID>(ctx, vw, E, vw.g.nx == ctx->g.nx, z_in, res_out, -1, fa);
     return launch_fused_tt<float, 16, 16, false, 2, FUSE_RESID>(ctx, vw, E, vw.g.nx == ctx->g.nx, z_in, res_out, -1, fa);
 }
 OpView fine_view(const esimp_ctx* ctx) {
