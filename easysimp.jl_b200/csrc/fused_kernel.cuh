@@ -119,16 +119,16 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 #else
-// host emulation: the copy happens at once (a legal completion order: every consumer sits behind wait_group + barrier)
-inline void cp_async8(void* smem_dst, const void* gsrc, bool valid) {
-    if (valid) memcpy(smem_dst, gsrc, 8); else memset(smem_dst, 0, 8);
-}
-inline void cp_async4(void* smem_dst, const void* gsrc, bool valid) {
-    if (valid) memcpy(smem_dst, gsrc, 4); else memset(smem_dst, 0, 4);
-}
-inline void cp_async_commit() {}
+// host emulation (selftest_kernel_host.cpp): either the copy happens at once, or -- deferred mode -- it is queued per
+// thread and only lands when cp_async_wait<N> retires its group, the LATEST moment the hardware may complete it.  A
+// kernel that is right in both modes reads no asynchronously copied datum before its wait_group + barrier.
+inline void cp_async8(void* smem_dst, const void* gsrc, bool valid) { emu_cp_async(smem_dst, gsrc, 8, valid); }
+inline void cp_async4(void* smem_dst, const void* gsrc, bool valid) { emu_cp_async(smem_dst, gsrc, 4, valid); }
+inline void cp_async_commit() { emu_cp_commit(); }
 template <int N>
-inline void cp_async_wait() {}
+inline void cp_async_wait() {
+    emu_cp_wait(N);
+}
 #endif
 // one scalar of the kernel's arithmetic type
 __device__ __forceinline__ void cp_async_scalar(double* smem_dst, const double* gsrc, bool valid) { cp_async8(smem_dst, gsrc, valid); }

@@ -46,6 +46,42 @@ inline void atomicAdd(T* p, T v) {
 double c_B[8][3][3];
 float c_Bf[8][3][3];
 
+// ---- cp.async model: immediate (copies land at issue) or deferred (they land when wait_group retires their group)
+static bool g_deferred_copies = false;
+struct EmuCopy {
+    void* dst;
+    const void* src;
+    int bytes;
+    bool valid;
+};
+static thread_local std::vector<std::vector<EmuCopy>> t_groups;  // committed groups, oldest first
+static thread_local std::vector<EmuCopy> t_open;                 // copies issued since the last commit
+inline void emu_apply(const EmuCopy& c) {
+    if (c.valid)
+        memcpy(c.dst, c.src, c.bytes);
+    else
+        memset(c.dst, 0, c.bytes);
+}
+inline void emu_cp_async(void* dst, const void* src, int bytes, bool valid) {
+    EmuCopy c{dst, src, bytes, valid};
+    if (g_deferred_copies)
+        t_open.push_back(c);
+    else
+        emu_apply(c);
+}
+inline void emu_cp_commit() {
+    if (!g_deferred_copies) return;
+    t_groups.push_back(t_open);
+    t_open.clear();
+}
+inline void emu_cp_wait(int n_pending_allowed) {  // cp.async.wait_group N: all but the N newest groups are complete
+    if (!g_deferred_copies) return;
+    while ((int)t_groups.size() > n_pending_allowed) {
+        for (const EmuCopy& c : t_groups.front()) emu_apply(c);
+        t_groups.erase(t_groups.begin());
+    }
+}
+
 #include "grid_dev.h"
 
 // the fused dot product: every thread of every block contributes its partial sum
@@ -210,6 +246,7 @@ int emu_fused_tile(int ty, int tz, int nx, int ny, int nz, int chunk, const doub
 
 
 int emu_pat(int q, int c, int d) { return pat(q, c, d) ? 1 : 0; }
+void emu_set_deferred_copies(int on) { g_deferred_copies = on != 0; }
 
 // plain FP64 operator on ONE x-slab of a partitioned grid: the caller passes the slab geometry esimp_set_grid_structured
 // builds (gp0, NPX, ge0, NEX, owned planes [ps0, ps1), visited layers [le0, le1)) and the slab's local arrays

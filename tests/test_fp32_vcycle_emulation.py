@@ -29,6 +29,7 @@ def emu():
     assert path.exists(), "run __graft_entry__.build() first"
     lib = C.CDLL(str(path))
     lib.emu_fused.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, D, D, D, D, D, D, C.c_double, C.c_double, D, D]
+    lib.emu_set_deferred_copies(1)  # the stricter cp.async model (see test_kernel_emulation.py)
     lib.emu_k32_restrict.argtypes = [C.c_int, C.c_int, C.c_int, F, U8, F]
     lib.emu_k32_prolong_add.argtypes = [C.c_int, C.c_int, C.c_int, F, U8, F]
     lib.emu_k32_cheb_first.argtypes = [C.c_longlong, F, F, C.c_float, F, F]

@@ -16,13 +16,16 @@ D = C.POINTER(C.c_double)
 PLAIN, DOT, SMOOTH, RESID, SMOOTH_DOT = range(5)
 
 
-@pytest.fixture(scope="module")
-def emu():
+@pytest.fixture(scope="module", params=["copies_land_at_issue", "copies_land_at_wait_group"])
+def emu(request):
+    """both extremes of cp.async completion: at once, or only when cp.async.wait_group retires the group (a kernel that
+    is right under both never reads an asynchronously copied datum before its wait + barrier)"""
     path = ROOT / "easysimp.jl_b200" / "libesimp_kernel_emu.so"
     assert path.exists(), "run __graft_entry__.build() first"
     lib = C.CDLL(str(path))
     lib.emu_fused.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, D, D, D, D, D, D, C.c_double, C.c_double, D, D]
     lib.emu_pat.argtypes = [C.c_int] * 3
+    lib.emu_set_deferred_copies(int(request.param == "copies_land_at_wait_group"))
     lib.emu_fused_tile.argtypes = [C.c_int] * 6 + [D, D, D, D]
     lib.emu_fused_slab.argtypes = [C.c_int] * 12 + [D, D, D, D]
     return lib
