@@ -30,6 +30,7 @@ __constant__ double c_B[8][3][3];   // mode-space blocks per parity class
 __constant__ float c_Bf[8][3][3];   // the same in single precision (FP32 multigrid cycle, multigrid32.cu)
 __constant__ double c_kdiag[3];     // K0[3a+c,3a+c] (same for every node a of a cuboid)
 static const esimp_ctx* g_const_owner = nullptr;
+static const esimp_ctx* g_const_owner_f32 = nullptr;  // owner of c_Bf (uploaded only when the FP32 cycle is used)
 
 #include "fused_kernel.cuh"
 
@@ -114,6 +115,7 @@ void tet4_element_matrix(const double* xyz, double lam, double mu, double* ke) {
 // a destroyed context must not be mistaken for the owner of the constants by a later one at the same address
 void hex8_forget_ctx(const esimp_ctx* ctx) {
     if (g_const_owner == ctx) g_const_owner = nullptr;
+    if (g_const_owner_f32 == ctx) g_const_owner_f32 = nullptr;
 }
 
 // Build K0 (unit modulus), its mode-space blocks and the nodal diagonal for the context's cuboid.
@@ -163,11 +165,6 @@ int hex8_upload_constants(esimp_ctx* ctx) {
     if (g_const_owner != ctx) {
         ESIMP_CUDA(cudaMemcpyToSymbolAsync(c_K0, ctx->K0, sizeof(ctx->K0), 0, cudaMemcpyHostToDevice, ctx->stream));
         ESIMP_CUDA(cudaMemcpyToSymbolAsync(c_B, ctx->B, sizeof(ctx->B), 0, cudaMemcpyHostToDevice, ctx->stream));
-        static float Bf[8][3][3];  // static: the asynchronous copy reads it after this function returns
-        for (int q = 0; q < 8; ++q)
-            for (int c = 0; c < 3; ++c)
-                for (int d = 0; d < 3; ++d) Bf[q][c][d] = (float)ctx->B[q][c][d];
-        ESIMP_CUDA(cudaMemcpyToSymbolAsync(c_Bf, Bf, sizeof(Bf), 0, cudaMemcpyHostToDevice, ctx->stream));
         ESIMP_CUDA(cudaMemcpyToSymbolAsync(c_kdiag, ctx->kdiag, sizeof(ctx->kdiag), 0, cudaMemcpyHostToDevice, ctx->stream));
         g_const_owner = ctx;
     }
@@ -324,9 +321,23 @@ int hex8_resid_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double
     return launch_fused_t<16, 16, false, 2, FUSE_RESID>(ctx, vw, z_in, res_out, -1, fa);
 }
 // ---- single-precision instances for the FP32 multigrid cycle (multigrid32.cu): same kernel, T = float
+static int upload_constants_f32(esimp_ctx* ctx) {
+    const bool stale = !ctx->k0_valid;  // hex8_upload_constants recomputes B then
+    ESIMP_TRY(hex8_upload_constants(ctx));
+    if (stale || g_const_owner_f32 != ctx) {
+        float Bf[8][3][3];
+        for (int q = 0; q < 8; ++q)
+            for (int c = 0; c < 3; ++c)
+                for (int d = 0; d < 3; ++d) Bf[q][c][d] = (float)ctx->B[q][c][d];
+        // stream ordered like the FP64 constants; a pageable source is staged before the call returns, so a local is fine
+        ESIMP_CUDA(cudaMemcpyToSymbolAsync(c_Bf, Bf, sizeof(Bf), 0, cudaMemcpyHostToDevice, ctx->stream));
+        g_const_owner_f32 = ctx;
+    }
+    return ESIMP_OK;
+}
 int hex8_smooth_view_f32(esimp_ctx* ctx, const OpView& vw, const float* E, const float* z_in, float* z_out, const float* r,
                          const float* dinv, float* d, float c1, float c2) {
-    ESIMP_TRY(hex8_upload_constants(ctx));
+    ESIMP_TRY(upload_constants_f32(ctx));
     FuseArgsT<float> fa;
     fa.r = r;
     fa.dinv = dinv;
@@ -339,7 +350,7 @@ int hex8_smooth_view_f32(esimp_ctx* ctx, const OpView& vw, const float* E, const
     return launch_fused_tt<float, 16, 16, false, 2, FUSE_SMOOTH>(ctx, vw, E, vw.g.nx == ctx->g.nx, z_in, z_out, -1, fa);
 }
 int hex8_resid_view_f32(esimp_ctx* ctx, const OpView& vw, const float* E, const float* z_in, float* res_out, const float* r) {
-    ESIMP_TRY(hex8_upload_constants(ctx));
+    ESIMP_TRY(upload_constants_f32(ctx));
     FuseArgsT<float> fa;
     fa.r = r;
     static const bool three = getenv("ESIMP_F32_CTAS") && atoi(getenv("ESIMP_F32_CTAS")) == 3;
