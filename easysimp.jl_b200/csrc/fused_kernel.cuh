@@ -185,13 +185,13 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
     const long long plane = g.plane, plane3 = 3 * g.plane;
 
     // running pointers (strength-reduced addressing: one add per plane)
-    const T* pu = u + (long long)pl0 * plane3 + (node_ok ? (long long)ey * (g.nz + 1) + ez : 0);
-    const T* ph = u + (long long)pl0 * plane3 + (halo_ok ? (long long)hy * (g.nz + 1) + hz : 0);
+    const T* pu = u + (long long)pl0 * plane3 + (node_ok ? (long long)ey * g.nzp + ez : 0);
+    const T* ph = u + (long long)pl0 * plane3 + (halo_ok ? (long long)hy * g.nzp + hz : 0);
     const T* pE = E + (long long)Lstart * g.eplane + (cell_ok ? (long long)ey * g.nz + ez : 0);
-    T* py = y + (long long)pl0 * plane3 + (node_ok ? (long long)ey * (g.nz + 1) + ez : 0);
-    T* pyh = y + (long long)pl0 * plane3 + (halo_ok ? (long long)hy * (g.nz + 1) + hz : 0);
+    T* py = y + (long long)pl0 * plane3 + (node_ok ? (long long)ey * g.nzp + ez : 0);
+    T* pyh = y + (long long)pl0 * plane3 + (halo_ok ? (long long)hy * g.nzp + hz : 0);
     const bool own_store = node_ok && ty >= 1 && tz >= 1;
-    long long foff = (long long)pl0 * plane3 + (node_ok ? (long long)ey * (g.nz + 1) + ez : 0);  // same offset as py
+    long long foff = (long long)pl0 * plane3 + (node_ok ? (long long)ey * g.nzp + ez : 0);  // same offset as py
 
     // zero the output tiles once (their borders are never written again)
     for (int i = tid; i < 2 * 9 * (TY + 1) * (TZ + 1); i += TY * TZ) (&sm.out[0][0][0][0][0])[i] = T(0);

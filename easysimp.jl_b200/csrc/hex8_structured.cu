@@ -209,8 +209,8 @@ template <int TY, int TZ>
 __global__ void k_zero_perimeter(GridDev g, int ps0, int ps1, double* __restrict__ y) {
     long long n = (long long)(ps1 - ps0) * 3 * g.plane;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        int k = (int)(i % (g.nz + 1));
-        int j = (int)((i / (g.nz + 1)) % (g.ny + 1));
+        int k = (int)(i % g.nzp);
+        int j = (int)((i / g.nzp) % (g.ny + 1));
         if ((j % TY) == 0 || (k % TZ) == 0) y[(long long)ps0 * 3 * g.plane + i] = 0.0;
     }
 }
@@ -380,8 +380,9 @@ __global__ void k_diag(GridDev g, int ps0, int ps1, int NEX, const double* __res
     long long n = (long long)(ps1 - ps0) * g.plane;
     double acc[1] = {0.0};
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        int k = (int)(i % (g.nz + 1));
-        int j = (int)((i / (g.nz + 1)) % (g.ny + 1));
+        int k = (int)(i % g.nzp);
+        if (k > g.nz) continue;  // row pads: no node (their diag / dinv entries stay zero)
+        int j = (int)((i / g.nzp) % (g.ny + 1));
         int lp = ps0 + (int)(i / g.plane);
         double s = 0.0;
 #pragma unroll
@@ -419,7 +420,7 @@ __global__ void k_diag_invert(GridDev g, int ps0, int ps1, const uint8_t* __rest
         int lp = (int)(d / (3 * g.plane));
         int c = (int)((d / g.plane) % 3);
         long long nn = (long long)lp * g.plane + d % g.plane;
-        bool fixed = (mask[nn] >> c) & 1;
+        bool fixed = ((mask[nn] >> c) & 1) || (int)(d % g.nzp) > g.nz;  // row pads: dinv = 0 like prescribed dofs
         dinv[d] = fixed ? 0.0 : 1.0 / dinv[d];  // 0: prescribed dofs never move (r = 0 there; the fused smoother relies on it)
     }
 }

@@ -40,8 +40,9 @@ __global__ void k32_restrict(GridDev gf, GridDev gc, int cp0, int cp1, const flo
                              const uint8_t* __restrict__ maskc, float* __restrict__ rc) {
     long long n = (long long)(cp1 - cp0) * 3 * gc.plane;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
-        int K = (int)(idx % (gc.nz + 1));
-        long long t = idx / (gc.nz + 1);
+        int K = (int)(idx % gc.nzp);
+        if (K > gc.nz) continue;  // pad entries of the node rows stay zero
+        long long t = idx / gc.nzp;
         int J = (int)(t % (gc.ny + 1));
         t /= (gc.ny + 1);
         int c = (int)(t % 3);
@@ -74,7 +75,7 @@ __global__ void k32_restrict(GridDev gf, GridDev gc, int cp0, int cp1, const flo
 // (J,K) position of a (plane, component), updating the 2x2 patch of fine nodes (2J+a, 2K+b)
 __global__ void __launch_bounds__(256) k32_prolong_add(GridDev gf, GridDev gc, int fp0, int fp1, const float* __restrict__ zc,
                                                        const uint8_t* __restrict__ maskf, float* __restrict__ zf) {
-    const int nJ = gc.ny + 1, nK = gc.nz + 1, nJK = nJ * nK, nzf = gf.nz + 1;
+    const int nJ = gc.ny + 1, nK = gc.nz + 1, nJK = nJ * nK, nzf = gf.nzp, nzc = gc.nzp;  // nK counts, nzf / nzc are row pitches
     for (int pc = blockIdx.y; pc < (fp1 - fp0) * 3; pc += gridDim.y) {
         const int lp = fp0 + pc / 3, c = pc % 3;
         const int Gf = gf.gp0 + lp;
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(256) k32_prolong_add(GridDev gf, GridDev gc, i
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nJK; i += gridDim.x * blockDim.x) {
             const int J = i / nK, K = i - J * nK;
             const bool hasJ = J < gc.ny, hasK = K < gc.nz;
-            const int o00 = J * nK + K, o01 = o00 + (hasK ? 1 : 0), o10 = o00 + (hasJ ? nK : 0), o11 = o10 + (hasK ? 1 : 0);
+            const int o00 = J * nzc + K, o01 = o00 + (hasK ? 1 : 0), o10 = o00 + (hasJ ? nzc : 0), o11 = o10 + (hasK ? 1 : 0);
             float v00 = c0[o00], v01 = c0[o01], v10 = c0[o10], v11 = c0[o11];
             if (two) {
                 v00 = 0.5f * (v00 + c1[o00]);

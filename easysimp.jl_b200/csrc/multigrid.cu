@@ -61,8 +61,9 @@ __global__ void k_restrict(GridDev gf, GridDev gc, int cp0, int cp1, const doubl
                            const uint8_t* __restrict__ maskc, double* __restrict__ rc) {
     long long n = (long long)(cp1 - cp0) * 3 * gc.plane;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
-        int K = (int)(idx % (gc.nz + 1));
-        long long t = idx / (gc.nz + 1);
+        int K = (int)(idx % gc.nzp);
+        if (K > gc.nz) continue;  // pad entries of the node rows stay zero
+        long long t = idx / gc.nzp;
         int J = (int)(t % (gc.ny + 1));
         t /= (gc.ny + 1);
         int c = (int)(t % 3);
@@ -98,7 +99,7 @@ __global__ void k_restrict(GridDev gf, GridDev gc, int cp0, int cp1, const doubl
 // Along each axis the parents of fine index i are i>>1 and (i+1)>>1 with weight 1/2 each (the same node if i is even).
 __global__ void __launch_bounds__(256) k_prolong_add(GridDev gf, GridDev gc, int fp0, int fp1, const double* __restrict__ zc,
                                                      const uint8_t* __restrict__ maskf, double* __restrict__ zf) {
-    const int nJ = gc.ny + 1, nK = gc.nz + 1, nJK = nJ * nK, nzf = gf.nz + 1;
+    const int nJ = gc.ny + 1, nK = gc.nz + 1, nJK = nJ * nK, nzf = gf.nzp, nzc = gc.nzp;  // nK counts, nzf / nzc are row pitches
     for (int pc = blockIdx.y; pc < (fp1 - fp0) * 3; pc += gridDim.y) {
         const int lp = fp0 + pc / 3, c = pc % 3;
         const int Gf = gf.gp0 + lp;
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(256) k_prolong_add(GridDev gf, GridDev gc, int
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nJK; i += gridDim.x * blockDim.x) {
             const int J = i / nK, K = i - J * nK;
             const bool hasJ = J < gc.ny, hasK = K < gc.nz;  // the last coarse row / column only owns the even fine index
-            const int o00 = J * nK + K, o01 = o00 + (hasK ? 1 : 0), o10 = o00 + (hasJ ? nK : 0), o11 = o10 + (hasK ? 1 : 0);
+            const int o00 = J * nzc + K, o01 = o00 + (hasK ? 1 : 0), o10 = o00 + (hasJ ? nzc : 0), o11 = o10 + (hasK ? 1 : 0);
             double v00 = c0[o00], v01 = c0[o01], v10 = c0[o10], v11 = c0[o11];
             if (two) {
                 v00 = 0.5 * (v00 + c1[o00]);
@@ -164,7 +165,7 @@ __global__ void k_pi_init(GridDev g, const uint8_t* __restrict__ mask, double* _
         int c = (int)((i / g.plane) % 3);
         long long nn = (i / (3 * g.plane)) * g.plane + i % g.plane;
         double v = (double)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5;
-        x[i] = ((mask[nn] >> c) & 1) ? 0.0 : v;
+        x[i] = (((mask[nn] >> c) & 1) || (int)(i % g.nzp) > g.nz) ? 0.0 : v;  // prescribed dofs and row pads stay zero
     }
 }
 __global__ void k_pi_scale(const double* __restrict__ q, const double* __restrict__ dinv, double* __restrict__ y, long long i0,
@@ -328,7 +329,8 @@ static int mg_build_levels(esimp_ctx* ctx) {
         g.ge0 = ex0 - left;
         g.NEX = (ex1 - ex0) + left + right;
         g.e2p = g.ge0 - g.gp0;
-        g.plane = (long long)(ny + 1) * (nz + 1);
+        g.nzp = esimp_node_pitch(nz);
+        g.plane = (long long)(ny + 1) * g.nzp;
         g.eplane = (long long)ny * nz;
         L.vw.own_p0 = left;
         L.vw.own_p1 = g.NPX - right;

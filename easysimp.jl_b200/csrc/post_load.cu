@@ -53,7 +53,8 @@ __global__ void k_body_force(GridDev g, int own_p0, int own_p1, const double* __
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
         const int lp = (int)(idx / g.plane);
         const int rem = (int)(idx % g.plane);
-        const int j = rem / (g.nz + 1), k = rem % (g.nz + 1);
+        const int j = rem / g.nzp, k = rem % g.nzp;
+        if (k > g.nz) continue;  // row pads
         double s = 0.0;
         if (lp >= own_p0 && lp < own_p1) {
             for (int dl = -1; dl <= 0; ++dl) {

@@ -148,7 +148,8 @@ GridDev level_grid(int nx, int ny, int nz) {
     g.NPX = nx + 1;
     g.NEX = nx;
     g.gp0 = g.ge0 = g.e2p = 0;
-    g.plane = (long long)(ny + 1) * (nz + 1);
+    g.nzp = nz + 1;  // the emulation keeps the unpadded pitch: the tests build their device-layout arrays with numpy reshapes
+    g.plane = (long long)(ny + 1) * g.nzp;
     g.eplane = (long long)ny * nz;
     return g;
 }
@@ -225,7 +226,8 @@ int emu_fused_tile(int ty, int tz, int nx, int ny, int nz, int chunk, const doub
     g.NPX = nx + 1;
     g.NEX = nx;
     g.gp0 = g.ge0 = g.e2p = 0;
-    g.plane = (long long)(ny + 1) * (nz + 1);
+    g.nzp = nz + 1;  // the emulation keeps the unpadded pitch: the tests build their device-layout arrays with numpy reshapes
+    g.plane = (long long)(ny + 1) * g.nzp;
     g.eplane = (long long)ny * nz;
     for (int q = 0; q < 8; ++q)
         for (int c = 0; c < 3; ++c)
@@ -261,7 +263,8 @@ int emu_fused_slab(int nx, int ny, int nz, int gp0, int npx, int ge0, int nex, i
     g.gp0 = gp0;
     g.ge0 = ge0;
     g.e2p = ge0 - gp0;
-    g.plane = (long long)(ny + 1) * (nz + 1);
+    g.nzp = nz + 1;  // the emulation keeps the unpadded pitch: the tests build their device-layout arrays with numpy reshapes
+    g.plane = (long long)(ny + 1) * g.nzp;
     g.eplane = (long long)ny * nz;
     for (int q = 0; q < 8; ++q)
         for (int c = 0; c < 3; ++c)
@@ -307,7 +310,8 @@ int emu_fused(int is_float, int mode, int nx, int ny, int nz, int chunk, const d
     g.NPX = nx + 1;
     g.NEX = nx;
     g.gp0 = g.ge0 = g.e2p = 0;
-    g.plane = (long long)(ny + 1) * (nz + 1);
+    g.nzp = nz + 1;  // the emulation keeps the unpadded pitch: the tests build their device-layout arrays with numpy reshapes
+    g.plane = (long long)(ny + 1) * g.nzp;
     g.eplane = (long long)ny * nz;
     const long long nd = 3 * g.NPX * g.plane, nc = (long long)g.NEX * g.eplane;
     for (int q = 0; q < 8; ++q)

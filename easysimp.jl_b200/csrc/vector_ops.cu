@@ -17,9 +17,11 @@ int esimp_fail(esimp_ctx* ctx, int code, const std::string& msg);
 
 // ---------------------------------------------------------------------------- numbering maps
 // device dof index -> caller dof index (structured grids)
+// returns -1 for the pad entries of a node row (k > nz): they carry no dof
 __device__ __forceinline__ long long caller_dof(const GridDev& g, const long long* __restrict__ dof_of_node, long long d) {
-    int k = (int)(d % (g.nz + 1));
-    long long t = d / (g.nz + 1);
+    int k = (int)(d % g.nzp);
+    if (k > g.nz) return -1;
+    long long t = d / g.nzp;
     int j = (int)(t % (g.ny + 1));
     t /= (g.ny + 1);
     int c = (int)(t % 3);
@@ -38,12 +40,18 @@ __device__ __forceinline__ long long caller_cell(const GridDev& g, long long e) 
 __global__ void k_gather_dofs(GridDev g, const long long* __restrict__ map, const double* __restrict__ src,
                               double* __restrict__ dst, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        dst[i] = src[caller_dof(g, map, i)];
+    {
+        const long long s = caller_dof(g, map, i);
+        dst[i] = s >= 0 ? src[s] : 0.0;
+    }
 }
 __global__ void k_scatter_dofs(GridDev g, const long long* __restrict__ map, const double* __restrict__ src,
                                double* __restrict__ dst, long long i0, long long i1) {
     for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (long long)gridDim.x * blockDim.x)
-        dst[caller_dof(g, map, i)] = src[i];
+    {
+        const long long s = caller_dof(g, map, i);
+        if (s >= 0) dst[s] = src[i];
+    }
 }
 __global__ void k_gather_cells(GridDev g, const double* __restrict__ src, double* __restrict__ dst, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
