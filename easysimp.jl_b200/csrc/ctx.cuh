@@ -200,6 +200,7 @@ int hex8_diagonal_view(esimp_ctx* ctx, const OpView& vw, double* dinv, long long
 int hex8_smooth_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double* z_out, const double* r, const double* dinv,
                      double* d, double c1, double c2, int dot_slot = -1);
 int hex8_resid_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double* res_out, const double* r);
+bool hex8_sweep_eligible(const esimp_ctx* ctx, const OpView& vw);
 int hex8_smooth_view_f32(esimp_ctx* ctx, const OpView& vw, const float* E, const float* z_in, float* z_out, const float* r,
                          const float* dinv, float* d, float c1, float c2);
 int hex8_resid_view_f32(esimp_ctx* ctx, const OpView& vw, const float* E, const float* z_in, float* res_out, const float* r);

@@ -16,6 +16,7 @@
 // the 2-D transform of a node plane is shared by the two cells either side of it, and the
 // x-direction butterfly of the output is shared the same way, so a cell costs 162 FP64 issue
 // slots instead of 600 and each u value is read from HBM once.
+#include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -33,6 +34,7 @@ static const esimp_ctx* g_const_owner = nullptr;
 static const esimp_ctx* g_const_owner_f32 = nullptr;  // owner of c_Bf (uploaded only when the FP32 cycle is used)
 
 #include "fused_kernel.cuh"
+#include "sweep_kernel.cuh"
 
 
 static const double HEXREF[8][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1},
@@ -264,6 +266,120 @@ static int launch_fused_tt(esimp_ctx* ctx, const OpView& vw, const T* E_t, bool 
     return ESIMP_OK;
 }
 
+
+// ---------------------------------------------------------------------------- the z-sweeping TMA kernel (sweep_kernel.cuh)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess) p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+// rank-3 FP64 tensor map: dims / strides in elements (innermost first), no swizzle, out-of-bounds elements read as zero
+static int make_map3(esimp_ctx* ctx, CUtensorMap* tm, const void* base, cuuint64_t d0, cuuint64_t d1, cuuint64_t d2, cuuint64_t s1, cuuint64_t s2,
+                     cuuint32_t b0, cuuint32_t b1, cuuint32_t b2) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return esimp_fail(ctx, ESIMP_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    cuuint64_t dim[3] = {d0, d1, d2}, stride[2] = {s1 * 8, s2 * 8};
+    cuuint32_t box[3] = {b0, b1, b2}, es[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dim, stride, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return esimp_fail(ctx, ESIMP_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return ESIMP_OK;
+}
+// the sweep kernel needs 16-byte strides (even nz for the modulus rows; the node rows are padded) and enough work per CTA
+bool hex8_sweep_eligible(const esimp_ctx* ctx, const OpView& vw) {
+    static const int env = getenv("ESIMP_SWEEP") ? atoi(getenv("ESIMP_SWEEP")) : 1;
+    if (!env) return false;
+    const int v = ctx->prm.matvec_variant;
+    if (v != ESIMP_MATVEC_AUTO && v != ESIMP_MATVEC_SWEEP) return false;
+    const GridDev& g = vw.g;
+    if ((g.nz % 2) != 0 || (g.nzp % 2) != 0) return false;  // TMA strides are multiples of 16 bytes
+    if (v == ESIMP_MATVEC_SWEEP) return true;                // asked for by name: any size (tests)
+    return g.nz >= 64 && g.ny >= 30 && vw.own_p1 - vw.own_p0 >= 8;
+}
+template <int MODE>
+static int launch_sweep(esimp_ctx* ctx, const OpView& vw, bool fine, const double* d_in, double* d_out, int dot_slot, const FuseArgs& fa) {
+    using TR = SweepTraits<MODE>;
+    using Smem = SweepSmem<TR::NF, TR::RING>;
+    const GridDev& g = vw.g;
+    const int nplanes = vw.own_p1 - vw.own_p0;
+    const int nty = (g.ny + 1 + SW_CROWS - 2) / (SW_CROWS - 1);
+    // x chunks: one CTA per SM; pick the chunk count whose waves x (planes per chunk + restart cost) is smallest
+    const int smem_limit = 232448 - 1024;
+    const int max_chunk = std::min(nplanes, (int)((smem_limit - (int)sizeof(Smem)) / (SW_CARRY_ROW * 8)) - 3);
+    int chunk = std::max(1, max_chunk);
+    {
+        double best = 1e300;
+        for (int nchunk = 1; nchunk <= nplanes; ++nchunk) {
+            const int c = (nplanes + nchunk - 1) / nchunk;
+            if (c > max_chunk) continue;
+            const int nc = (nplanes + c - 1) / c;
+            const double waves = ceil((double)nty * nc / 148.0);
+            const double cost = waves * (c + 3.0);
+            if (cost < best - 1e-9) {
+                best = cost;
+                chunk = c;
+            }
+            if (c <= 4) break;
+        }
+    }
+    if (ctx->fused_chunk > 0) chunk = std::min(ctx->fused_chunk, std::max(1, max_chunk));
+    const int nchunk = (nplanes + chunk - 1) / chunk;
+    const size_t smem = sizeof(Smem) + (size_t)(chunk + 3) * SW_CARRY_ROW * 8;
+    static unsigned long long attr_devices = 0;
+    auto kern = k_matvec_sweep<MODE>;
+    const unsigned long long dev_bit = 1ull << (ctx->device & 63);
+    if (!(attr_devices & dev_bit)) {
+        ESIMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
+        attr_devices |= dev_bit;
+    }
+    SweepArgs a{};
+    a.g = g;
+    a.le0 = vw.mv_e0;
+    a.le1 = vw.mv_e1;
+    a.ps0 = vw.own_p0;
+    a.ps1 = vw.own_p1;
+    a.chunk = chunk;
+    a.y = d_out;
+    a.d_out = fa.d;
+    a.c1 = fa.c1;
+    a.c2 = fa.c2;
+    a.have_d = fa.c1 != 0.0 ? 1 : 0;
+    const long long nblk = (long long)nty * nchunk;
+    if (TR::DOT && nblk > ctx->partial_mv_cap) {
+        cudaFree(ctx->d_partial_mv);
+        ESIMP_CUDA(cudaMalloc(&ctx->d_partial_mv, sizeof(double) * nblk));
+        ctx->partial_mv_cap = nblk;
+    }
+    a.partial = ctx->d_partial_mv;
+    a.ticket = ctx->d_ticket + 2;
+    a.dot_out = RedOut<1>{{ctx->d_scal + (TR::DOT ? dot_slot : 0)}};
+    memcpy(a.blk.B, ctx->B, sizeof(ctx->B));
+    alignas(64) CUtensorMap tmU, tmE, tmR, tmDinv, tmD;
+    const cuuint64_t nz1 = g.nz + 1, ny1 = g.ny + 1, n3 = 3ull * g.NPX;
+    ESIMP_TRY(make_map3(ctx, &tmU, d_in, nz1, ny1, n3, g.nzp, g.plane, SW_BOXZ, SW_ROWS, 3));
+    ESIMP_TRY(make_map3(ctx, &tmE, vw.E, g.nz, g.ny, g.NEX, g.nz, g.eplane, 32, SW_CROWS, 1));
+    tmR = tmDinv = tmD = tmU;
+    if (TR::NF >= 1) ESIMP_TRY(make_map3(ctx, &tmR, fa.r, nz1, ny1, n3, g.nzp, g.plane, SW_BOXZ, SW_CROWS, 3));
+    if (TR::NF == 3) {
+        ESIMP_TRY(make_map3(ctx, &tmDinv, fa.dinv, nz1, ny1, n3, g.nzp, g.plane, SW_BOXZ, SW_CROWS, 3));
+        ESIMP_TRY(make_map3(ctx, &tmD, fa.d, nz1, ny1, n3, g.nzp, g.plane, SW_BOXZ, SW_CROWS, 3));
+    }
+    const bool timed = ctx->prof_on && fine && 2 * ctx->prof_n + 1 < (int)ctx->prof_ev.size();
+    if (timed) ctx->prof_tag[ctx->prof_n] = MODE <= FUSE_DOT ? 0 : 1;
+    if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
+    kern<<<dim3(nty, nchunk), SW_THREADS, smem, ctx->stream>>>(a, tmU, tmE, tmR, tmDinv, tmD);
+    if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n++ + 1], ctx->stream);
+    ctx->launches++;
+    ESIMP_CUDA(cudaGetLastError());
+    return ESIMP_OK;
+}
+
 // the FP64 operator: modulus from the view, fine grid = the context's own modulus array
 template <int TY, int TZ, bool ATOMIC, int MINB, int MODE>
 static int launch_fused_t(esimp_ctx* ctx, const OpView& vw, const double* d_in, double* d_out, int dot_slot, const FuseArgs& fa = FuseArgs()) {
@@ -286,7 +402,12 @@ int hex8_matvec_view(esimp_ctx* ctx, const OpView& vw, const double* d_in, doubl
     ESIMP_TRY(hex8_upload_constants(ctx));
     const GridDev& g = vw.g;
     // 16x16 is the default: 8x16 (4 CTAs/SM) is 7 % faster in isolation but not inside the power-capped solve
-    if (variant == ESIMP_MATVEC_AUTO) variant = ESIMP_MATVEC_FUSED;
+    if ((variant == ESIMP_MATVEC_AUTO || variant == ESIMP_MATVEC_SWEEP) && hex8_sweep_eligible(ctx, vw)) {
+        const bool fine = vw.E == ctx->d_E;
+        return dot_slot >= 0 ? launch_sweep<FUSE_DOT>(ctx, vw, fine, d_in, d_out, dot_slot, FuseArgs())
+                             : launch_sweep<FUSE_PLAIN>(ctx, vw, fine, d_in, d_out, -1, FuseArgs());
+    }
+    if (variant == ESIMP_MATVEC_AUTO || variant == ESIMP_MATVEC_SWEEP) variant = ESIMP_MATVEC_FUSED;
     if (variant == ESIMP_MATVEC_DENSE_ATOMIC) {
         ESIMP_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * 3 * g.NPX * g.plane, ctx->stream));
         long long n = (long long)(vw.mv_e1 - vw.mv_e0) * g.eplane;
@@ -311,6 +432,11 @@ int hex8_smooth_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, doubl
     fa.d = d;
     fa.c1 = c1;
     fa.c2 = c2;
+    if (hex8_sweep_eligible(ctx, vw)) {
+        const bool fine = vw.E == ctx->d_E;
+        return dot_slot >= 0 ? launch_sweep<FUSE_SMOOTH_DOT>(ctx, vw, fine, z_in, z_out, dot_slot, fa)
+                             : launch_sweep<FUSE_SMOOTH>(ctx, vw, fine, z_in, z_out, -1, fa);
+    }
     if (dot_slot >= 0) return launch_fused_t<16, 16, false, 2, FUSE_SMOOTH_DOT>(ctx, vw, z_in, z_out, dot_slot, fa);
     return launch_fused_t<16, 16, false, 2, FUSE_SMOOTH>(ctx, vw, z_in, z_out, -1, fa);
 }
@@ -318,6 +444,7 @@ int hex8_resid_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double
     ESIMP_TRY(hex8_upload_constants(ctx));
     FuseArgs fa;
     fa.r = r;
+    if (hex8_sweep_eligible(ctx, vw)) return launch_sweep<FUSE_RESID>(ctx, vw, vw.E == ctx->d_E, z_in, res_out, -1, fa);
     return launch_fused_t<16, 16, false, 2, FUSE_RESID>(ctx, vw, z_in, res_out, -1, fa);
 }
 // ---- single-precision instances for the FP32 multigrid cycle (multigrid32.cu): same kernel, T = float

@@ -99,6 +99,115 @@ inline void grid_reduce(double (&v)[NV], double* partial, unsigned int* ticket, 
 #include "fused_kernel.cuh"
 #include "mg32_kernels.cuh"
 
+// ---------------------------------------------------------------------------------------------------------------------
+// emulation of what sweep_kernel.cuh uses beyond plain CUDA C++: mbarriers (phase / pending arrivals / transaction bytes),
+// 3-D TMA boxes with out-of-bounds zero fill, warp shuffles and warp barriers.  Two TMA models: the box lands at issue,
+// or a DMA thread delivers it a little later (a consumer that reads before its mbarrier wait then sees stale data).
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+struct SwBar {
+    std::atomic<unsigned> phase{0};
+    int count = 0, pending = 0;
+    long long tx = 0;
+};
+static std::mutex g_bar_mutex;
+static void emu_bar_check(SwBar* b) {
+    if (b->pending == 0 && b->tx == 0) {
+        b->pending = b->count;
+        b->phase.fetch_add(1, std::memory_order_release);
+    }
+}
+inline void sw_bar_init(SwBar* b, int count) {
+    new (b) SwBar();
+    b->count = b->pending = count;
+}
+inline void sw_fence_init() {}
+inline void sw_bar_arrive(SwBar* b) {
+    std::lock_guard<std::mutex> lock(g_bar_mutex);
+    b->pending--;
+    emu_bar_check(b);
+}
+inline void sw_bar_expect_tx(SwBar* b, unsigned bytes) {
+    std::lock_guard<std::mutex> lock(g_bar_mutex);
+    b->tx += bytes;
+    b->pending--;
+    emu_bar_check(b);
+}
+inline void emu_bar_complete_tx(SwBar* b, long long bytes) {
+    std::lock_guard<std::mutex> lock(g_bar_mutex);
+    b->tx -= bytes;
+    emu_bar_check(b);
+}
+inline void sw_bar_wait(SwBar* b, unsigned parity) {
+    while ((b->phase.load(std::memory_order_acquire) & 1u) == (parity & 1u)) std::this_thread::yield();
+}
+typedef SwBar* SwBarAddr;
+inline SwBarAddr sw_bar_addr(const SwBar* b) { return const_cast<SwBar*>(b); }
+inline SwBarAddr sw_bar_at(SwBarAddr base, int index) { return base + index; }
+inline void sw_bar_arrive_a(SwBarAddr b) { sw_bar_arrive(b); }
+inline void sw_bar_wait_a(SwBarAddr b, unsigned parity) { sw_bar_wait(b, parity); }
+
+struct SwTensorMap {  // what cuTensorMapEncodeTiled would hold for a rank-3 FP64 tensor (strides in elements)
+    const double* base = nullptr;
+    long long dim[3] = {0, 0, 0}, stride[3] = {1, 0, 0};
+    int box[3] = {0, 0, 0};
+};
+struct EmuTmaJob {
+    double* dst;
+    SwTensorMap tm;  // by value: the kernel's by-value parameter lives on the issuing host thread's stack
+    int c[3];
+    SwBar* bar;
+};
+static bool g_tma_deferred = false;
+static std::mutex g_tma_mutex;
+static std::deque<EmuTmaJob> g_tma_queue;
+static void emu_tma_run(const EmuTmaJob& j) {
+    const SwTensorMap& t = j.tm;
+    long long n = 0;
+    for (int z = 0; z < t.box[2]; ++z)
+        for (int y = 0; y < t.box[1]; ++y)
+            for (int x = 0; x < t.box[0]; ++x, ++n) {
+                const long long gx = j.c[0] + x, gy = j.c[1] + y, gz = j.c[2] + z;
+                const bool in = gx >= 0 && gx < t.dim[0] && gy >= 0 && gy < t.dim[1] && gz >= 0 && gz < t.dim[2];
+                j.dst[n] = in ? t.base[gx * t.stride[0] + gy * t.stride[1] + gz * t.stride[2]] : 0.0;
+            }
+    emu_bar_complete_tx(j.bar, n * 8);
+}
+inline void sw_tma_3d(void* dst, const SwTensorMap* tm, int c0, int c1, int c2, SwBar* bar) {
+    EmuTmaJob j{(double*)dst, *tm, {c0, c1, c2}, bar};
+    if (!g_tma_deferred) {
+        emu_tma_run(j);
+    } else {
+        std::lock_guard<std::mutex> lock(g_tma_mutex);
+        g_tma_queue.push_back(j);
+    }
+}
+// warp-level primitives: one std::barrier and one exchange row per warp of the block
+static std::vector<std::unique_ptr<std::barrier<>>> g_warp_barrier;
+static double g_shfl_row[64][32];
+static std::barrier<>* g_consumer_barrier = nullptr;
+inline void sw_syncwarp() { g_warp_barrier[threadIdx.x >> 5]->arrive_and_wait(); }
+inline double sw_shfl_up1(double v) {
+    const int wp = threadIdx.x >> 5, ln = threadIdx.x & 31;
+    g_shfl_row[wp][ln] = v;
+    g_warp_barrier[wp]->arrive_and_wait();
+    const double r = ln > 0 ? g_shfl_row[wp][ln - 1] : v;
+    g_warp_barrier[wp]->arrive_and_wait();
+    return r;
+}
+inline void sw_regs_producer() {}
+inline void sw_regs_consumer() {}
+inline void sw_consumer_barrier() { g_consumer_barrier->arrive_and_wait(); }
+#define SW_PIN32(x) (void)(x)
+#define SW_PIN64(x) (void)(x)
+#define __grid_constant__
+alignas(128) unsigned char sw_smem_raw[512 * 1024];
+#define SW_SMEM_DECL
+#include "sweep_kernel.cuh"
+
 namespace {
 
 template <typename T, int MODE, int TY = 16, int TZ = 16>
@@ -353,5 +462,122 @@ int emu_fused(int is_float, int mode, int nx, int ny, int nz, int chunk, const d
     if (d)
         for (long long i = 0; i < nd; ++i) d[i] = df[i];
     return st;
+}
+
+void emu_set_deferred_tma(int on) { g_tma_deferred = on != 0; }
+
+// One launch of the sweep kernel (sweep_kernel.cuh) on ONE x-slab (or the whole grid: gp0 = ge0 = 0, npx = nx + 1, nex = nx,
+// [ps0, ps1) = [0, nx + 1), [le0, le1) = [0, nx)).  Vectors in the library's device layout with node-row pitch nzp.
+int emu_sweep(int mode, int nx, int ny, int nz, int nzp, int gp0, int npx, int ge0, int nex, int ps0, int ps1, int le0, int le1, int chunk,
+              const double* blocks, const double* E, const double* u, const double* r, const double* dinv, double* d, double c1, double c2,
+              double* y, double* dot) {
+    SweepArgs a{};
+    GridDev& g = a.g;
+    g.nx = nx;
+    g.ny = ny;
+    g.nz = nz;
+    g.NPX = npx;
+    g.NEX = nex;
+    g.gp0 = gp0;
+    g.ge0 = ge0;
+    g.e2p = ge0 - gp0;
+    g.nzp = nzp;
+    g.plane = (long long)(ny + 1) * nzp;
+    g.eplane = (long long)ny * nz;
+    a.le0 = le0;
+    a.le1 = le1;
+    a.ps0 = ps0;
+    a.ps1 = ps1;
+    const int nplanes = ps1 - ps0;
+    a.chunk = chunk > 0 ? chunk : nplanes;
+    a.y = y;
+    a.d_out = d;
+    a.c1 = c1;
+    a.c2 = c2;
+    a.have_d = c1 != 0.0;
+    double dummy = 0.0;
+    if (dot) *dot = 0.0;
+    a.dot_out = RedOut<1>{{dot ? dot : &dummy}};
+    for (int q = 0; q < 8; ++q)
+        for (int c = 0; c < 3; ++c)
+            for (int e = 0; e < 3; ++e) a.blk.B[q][c][e] = blocks[(q * 3 + c) * 3 + e];
+    auto node_map = [&](const double* base, int bz_, int by_) {
+        SwTensorMap t;
+        t.base = base;
+        t.dim[0] = nz + 1;
+        t.dim[1] = ny + 1;
+        t.dim[2] = 3LL * npx;
+        t.stride[0] = 1;
+        t.stride[1] = nzp;
+        t.stride[2] = g.plane;
+        t.box[0] = bz_;
+        t.box[1] = by_;
+        t.box[2] = 3;
+        return t;
+    };
+    SwTensorMap tmU = node_map(u, SW_BOXZ, SW_ROWS), tmR = node_map(r, SW_BOXZ, SW_CROWS), tmDinv = node_map(dinv, SW_BOXZ, SW_CROWS),
+                tmD = node_map(d, SW_BOXZ, SW_CROWS), tmE;
+    tmE.base = E;
+    tmE.dim[0] = nz;
+    tmE.dim[1] = ny;
+    tmE.dim[2] = nex;
+    tmE.stride[0] = 1;
+    tmE.stride[1] = nz;
+    tmE.stride[2] = g.eplane;
+    tmE.box[0] = 32;
+    tmE.box[1] = SW_CROWS;
+    tmE.box[2] = 1;
+    const int nty = (ny + 1 + SW_CROWS - 2) / (SW_CROWS - 1), nchunk = (nplanes + a.chunk - 1) / a.chunk;
+    gridDim = EmuDim3{(unsigned)nty, (unsigned)nchunk, 1};
+    blockDim = EmuDim3{(unsigned)SW_THREADS, 1, 1};
+    g_warp_barrier.clear();
+    for (int wi = 0; wi < SW_THREADS / 32; ++wi) g_warp_barrier.emplace_back(new std::barrier<>(32));
+    for (int by = 0; by < nchunk; ++by)
+        for (int bx = 0; bx < nty; ++bx) {
+            blockIdx = EmuDim3{(unsigned)bx, (unsigned)by, 0};
+            std::barrier<> barrier(SW_THREADS), cbarrier(32 * SW_NW);
+            g_barrier = &barrier;
+            g_consumer_barrier = &cbarrier;
+            std::atomic<bool> done{false};
+            std::thread dma([&] {  // deferred TMA model: boxes land a little after they were issued, in order
+                while (true) {
+                    EmuTmaJob j;
+                    bool have = false;
+                    {
+                        std::lock_guard<std::mutex> lock(g_tma_mutex);
+                        if (!g_tma_queue.empty()) {
+                            j = g_tma_queue.front();
+                            g_tma_queue.pop_front();
+                            have = true;
+                        }
+                    }
+                    if (have) {
+                        std::this_thread::sleep_for(std::chrono::microseconds(200));
+                        emu_tma_run(j);
+                    } else if (done.load()) {
+                        break;
+                    } else {
+                        std::this_thread::yield();
+                    }
+                }
+            });
+            std::vector<std::thread> threads;
+            threads.reserve(SW_THREADS);
+            for (int t = 0; t < SW_THREADS; ++t)
+                threads.emplace_back([&, t] {
+                    threadIdx = EmuDim3{(unsigned)t, 0, 0};
+                    switch (mode) {
+                        case FUSE_PLAIN: k_matvec_sweep<FUSE_PLAIN>(a, tmU, tmE, tmR, tmDinv, tmD); break;
+                        case FUSE_DOT: k_matvec_sweep<FUSE_DOT>(a, tmU, tmE, tmR, tmDinv, tmD); break;
+                        case FUSE_SMOOTH: k_matvec_sweep<FUSE_SMOOTH>(a, tmU, tmE, tmR, tmDinv, tmD); break;
+                        case FUSE_RESID: k_matvec_sweep<FUSE_RESID>(a, tmU, tmE, tmR, tmDinv, tmD); break;
+                        case FUSE_SMOOTH_DOT: k_matvec_sweep<FUSE_SMOOTH_DOT>(a, tmU, tmE, tmR, tmDinv, tmD); break;
+                    }
+                });
+            for (auto& th : threads) th.join();
+            done.store(true);
+            dma.join();
+        }
+    return 0;
 }
 }

@@ -1,0 +1,476 @@
+// sweep_kernel.cuh -- the z-sweeping, TMA-fed, dataflow-synchronised version of the fused hex8 operator (sm_100a).
+//
+// Same arithmetic as fused_kernel.cuh (mode-space blocks, x-march with the modulus folded into the x butterfly), different
+// machine mapping, built from what ncu said about the round-1 kernel (FP64 pipe 58 % busy, 1.27x redundant FP64 work on tile
+// perimeters, 287 non-FP64 issue slots per 324 FP64 ones, one CTA barrier per plane):
+//   * a CTA owns 15 node rows (16 cell rows: 8 warps, TWO stacked cells per thread) x ALL of z x one x chunk.  z is swept
+//     in segments of 32 cell columns (lanes); the z-high face contribution of lane 31 is carried to lane 0 of the next
+//     segment through shared memory, so z costs no recomputed perimeter at all (tile redundancy 16/15, not (16/15)^2);
+//   * two cells per thread share the z butterflies of their common node row, the y exchange of that row stays in
+//     registers, and every per-step overhead (barrier waits, constant loads, addressing) is paid once per two cells;
+//   * node planes, modulus tiles and the fused-update operands arrive by TMA (cp.async.bulk.tensor 3-D boxes issued by ONE
+//     thread of a producer warp, mbarrier complete_tx) -- no per-thread LDGSTS, no address arithmetic, out-of-range rows /
+//     columns / cells are zero-filled by the TMA unit (E = 0 kills every contribution of a cell that does not exist);
+//   * no CTA barrier in the loop: z neighbours exchange through warp shuffles, y neighbours (adjacent warps) through a
+//     double-buffered shared row with a full / empty mbarrier pair per warp, the input ring through full / empty mbarriers;
+//   * the 45 mode-space constants are kernel parameters (constant bank 0: direct DFMA operands, and no process-global
+//     __constant__ state shared between contexts).
+// Needs the padded node-row pitch of grid_dev.h (16-byte TMA strides) and an even nz (modulus rows); hex8_structured.cu
+// falls back to k_matvec_fused otherwise (coarse multigrid levels).
+// Compiled for the host as well (selftest_kernel_host.cpp: threads of a block as host threads, mbarriers / TMA / shuffles
+// emulated) so that the -m "not gpu" suite runs this very source against the oracle.
+#pragma once
+
+constexpr int SW_NW = 8;                // consumer warps; a thread owns the two stacked cells (rows 2w, 2w + 1) of a z column
+constexpr int SW_CROWS = 2 * SW_NW;     // cell rows of a tile; a tile owns SW_CROWS - 1 node rows
+constexpr int SW_ROWS = SW_CROWS + 1;   // node rows of an input box
+constexpr int SW_BOXZ = 34;             // node columns of a box: 32 + the z-high neighbour + 1 (16-byte multiple)
+constexpr int SW_PW = 4;                // producer warps: one whole warpgroup (setmaxnreg works per warpgroup); one thread of it issues
+constexpr int SW_THREADS = 32 * (SW_NW + SW_PW);
+constexpr int SW_IN_BOX = 3 * SW_ROWS * SW_BOXZ;                 // doubles in an input box {34, 17, 3}
+constexpr int SW_IN_SLOT = (SW_IN_BOX * 8 + 127) / 128 * 16;     // slot pitch in doubles: TMA destinations are 128-byte aligned
+constexpr int SW_OP_BOX = 3 * SW_CROWS * SW_BOXZ;                // operand box {34, 16, 3}: 13056 B = 102 * 128
+constexpr int SW_E_BOX = SW_CROWS * 32;                          // modulus box {32, 16, 1}
+
+struct SweepBlocks {
+    double B[8][3][3];
+};
+
+#ifndef ESIMP_HOST_EMULATION
+typedef unsigned long long SwBar;
+typedef CUtensorMap SwTensorMap;
+__device__ __forceinline__ unsigned sw_smem(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sw_bar_init(SwBar* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sw_smem(b)), "r"(count)); }
+__device__ __forceinline__ void sw_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void sw_bar_expect_tx(SwBar* b, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sw_smem(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void sw_bar_arrive(SwBar* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sw_smem(b)) : "memory"); }
+__device__ __forceinline__ void sw_bar_wait(SwBar* b, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nSW_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SW_DONE_%=;\nbra SW_WAIT_%=;\nSW_DONE_%=:\n}\n" ::"r"(sw_smem(b)),
+        "r"(parity)
+        : "memory");
+}
+// the same on precomputed 32-bit shared addresses (hot loop: no generic -> shared conversion, no address arithmetic)
+__device__ __forceinline__ void sw_bar_arrive_a(unsigned b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b) : "memory"); }
+__device__ __forceinline__ void sw_bar_wait_a(unsigned b, unsigned parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nSW_WAITA_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SW_DONEA_%=;\nbra SW_WAITA_%=;\nSW_DONEA_%=:\n}\n" ::"r"(b),
+        "r"(parity)
+        : "memory");
+}
+typedef unsigned SwBarAddr;
+__device__ __forceinline__ SwBarAddr sw_bar_addr(const SwBar* b) { return sw_smem(b); }
+__device__ __forceinline__ SwBarAddr sw_bar_at(SwBarAddr base, int index) { return base + 8u * (unsigned)index; }
+__device__ __forceinline__ void sw_tma_3d(void* dst, const SwTensorMap* tm, int c0, int c1, int c2, SwBar* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(sw_smem(dst)),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(sw_smem(bar))
+                 : "memory");
+}
+__device__ __forceinline__ double sw_shfl_up1(double v) {
+    const int lo = __shfl_up_sync(0xffffffffu, __double2loint(v), 1), hi = __shfl_up_sync(0xffffffffu, __double2hiint(v), 1);
+    return __hiloint2double(hi, lo);
+}
+// keep a thread-invariant value in its register: the compiler must not rematerialise it from %tid at every use
+#define SW_PIN32(x) asm volatile("" : "+r"(x))
+#define SW_PIN64(x) asm volatile("" : "+l"(x))
+__device__ __forceinline__ void sw_syncwarp() { __syncwarp(); }
+// register reallocation between the producer warpgroup and the two consumer warpgroups (168 per thread at launch)
+__device__ __forceinline__ void sw_regs_producer() { asm volatile("setmaxnreg.dec.sync.aligned.u32 40;\n"); }
+__device__ __forceinline__ void sw_regs_consumer() { asm volatile("setmaxnreg.inc.sync.aligned.u32 232;\n"); }
+__device__ __forceinline__ void sw_consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(32 * SW_NW) : "memory"); }
+#define SW_SMEM_DECL extern __shared__ __align__(128) unsigned char sw_smem_raw[]
+#endif
+
+template <int NF, int RING>
+struct SweepSmem {
+    alignas(128) double in[RING][SW_IN_SLOT];                             // node-plane boxes [c][17 rows][34]
+    alignas(128) double E[RING][SW_E_BOX];                                // modulus boxes [16 rows][32]
+    alignas(128) double fz[NF > 0 ? 2 : 1][NF > 0 ? NF : 1][SW_OP_BOX];   // r | r, Dinv, d boxes [c][16 rows][34]
+    // y-high mode coefficients (bz = 0, 1) of warp w's upper cell for node row 2w + 2 (warp w + 1).  One slot per input-ring
+    // slot, indexed like the plane it belongs to: warp w + 1 has read the slot before it releases that plane's input slot, and
+    // warp w cannot be RING planes ahead of a plane that is not released, so no "empty" barrier is needed for this exchange
+    double xch[RING][SW_NW][3][2][32];
+    SwBar full[RING], empty[RING], ffull[2], fempty[2], xfull[RING][SW_NW];
+};
+// the carry rows follow the struct: carry[ci][row][3] = z-high face sums of lane 31 (per node row, component), read by
+// lane 0 one segment later; row ci = 0 .. nsteps (output planes of the chunk)
+constexpr int SW_CARRY_ROW = SW_CROWS * 3;
+
+template <int MODE>
+struct SweepTraits {
+    static constexpr bool DOT = MODE == FUSE_DOT || MODE == FUSE_SMOOTH_DOT;
+    static constexpr bool SMOOTH = MODE == FUSE_SMOOTH || MODE == FUSE_SMOOTH_DOT;
+    static constexpr int NF = SMOOTH ? 3 : (MODE == FUSE_RESID ? 1 : 0);
+    static constexpr int RING = NF > 0 ? 4 : 5;
+};
+
+struct SweepArgs {
+    GridDev g;
+    int le0, le1, ps0, ps1, chunk;
+    double* y;        // result vector (owned nodes of the owned planes)
+    double* d_out;    // FUSE_SMOOTH: the Chebyshev direction is updated in place (read through the d tensor map)
+    double c1, c2;
+    int have_d;       // FUSE_SMOOTH: c1 != 0 (the first step of a sweep has no previous direction)
+    double* partial;
+    unsigned int* ticket;
+    RedOut<1> dot_out;
+    SweepBlocks blk;
+};
+
+// w = K~ v with the blocks taken from kernel parameters
+__device__ __forceinline__ void sw_apply_blocks(const SweepBlocks& blk, const double (&v)[3][8], double (&w)[3][8]) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            double acc = 0.0;
+            bool first = true;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                if (pat(q, c, d)) {
+                    if (first) {
+                        acc = blk.B[q][c][d] * v[d][q ^ (1 << d)];
+                        first = false;
+                    } else {
+                        acc = fma(blk.B[q][c][d], v[d][q ^ (1 << d)], acc);
+                    }
+                }
+            }
+            w[c][q ^ (1 << c)] = acc;
+        }
+    }
+}
+
+// one cell, one x step: Fn = y-z modes of the new plane from the z butterflies (zs, zd) of its two node rows; v = E (Fn +- Fp),
+// w = K~ v, A = contributions to the node plane this step completes (y-z mode space), Gpp = contributions to the next one
+__device__ __forceinline__ void sw_cell_step(const SweepBlocks& blk, const double (&zs0)[3], const double (&zd0)[3], const double (&zs1)[3],
+                                             const double (&zd1)[3], double Ee, const double (&Fp)[3][4], double (&Fn)[3][4],
+                                             double (&Gpp)[3][4], double (&A)[3][4]) {
+    double v[3][8], wv[3][8];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        Fn[c][0] = zs1[c] + zs0[c];
+        Fn[c][1] = zs1[c] - zs0[c];
+        Fn[c][2] = zd1[c] + zd0[c];
+        Fn[c][3] = zd1[c] - zd0[c];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const double ep = Ee * Fp[c][b];
+            v[c][2 * b] = fma(Ee, Fn[c][b], ep);
+            v[c][2 * b + 1] = fma(Ee, Fn[c][b], -ep);
+        }
+    }
+    sw_apply_blocks(blk, v, wv);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        A[c][0] = Gpp[c][0] - wv[c][1];  // wv[c][0] is the translation mode, structurally zero
+        Gpp[c][0] = wv[c][1];
+#pragma unroll
+        for (int b = 1; b < 4; ++b) {
+            A[c][b] = Gpp[c][b] + (wv[c][2 * b] - wv[c][2 * b + 1]);
+            Gpp[c][b] = wv[c][2 * b] + wv[c][2 * b + 1];
+        }
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(SW_THREADS, 1)
+    k_matvec_sweep(const __grid_constant__ SweepArgs a, const __grid_constant__ SwTensorMap tmU, const __grid_constant__ SwTensorMap tmE,
+                   const __grid_constant__ SwTensorMap tmR, const __grid_constant__ SwTensorMap tmDinv, const __grid_constant__ SwTensorMap tmD) {
+    using TR = SweepTraits<MODE>;
+    constexpr int NF = TR::NF, RING = TR::RING, NFS = NF > 0 ? NF : 1;
+    SW_SMEM_DECL;
+    SweepSmem<NF, RING>& sm = *reinterpret_cast<SweepSmem<NF, RING>*>(sw_smem_raw);
+    double* const carry = reinterpret_cast<double*>(sw_smem_raw + sizeof(SweepSmem<NF, RING>));
+    const GridDev& g = a.g;
+    int w = (int)(threadIdx.x >> 5) - SW_PW, lane = threadIdx.x & 31;  // w < 0: producer warpgroup, w = 0 .. 7: consumer warps
+    SW_PIN32(w);
+    SW_PIN32(lane);
+    const int Y0 = blockIdx.x * (SW_CROWS - 1) - 1;
+    const int P0 = a.ps0 + blockIdx.y * a.chunk, P1 = min(P0 + a.chunk, a.ps1);
+    const int Lstart = max(P0 - g.e2p - 1, a.le0), Lend = min(P1 - g.e2p, a.le1);
+    const int nsteps = Lend - Lstart, pl0 = Lstart + g.e2p;
+    const int nseg = (g.nz + 31) / 32;
+    const bool extra = (g.nz & 31) == 0;  // node column nz is nobody's own column: lane 31 of the last segment takes it along
+    double pq[1] = {0.0};
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < RING; ++s) {
+            sw_bar_init(&sm.full[s], 1);
+            sw_bar_init(&sm.empty[s], SW_NW);
+            for (int r = 0; r < SW_NW; ++r) sw_bar_init(&sm.xfull[s][r], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            sw_bar_init(&sm.ffull[s], 1);
+            sw_bar_init(&sm.fempty[s], SW_NW);
+        }
+        sw_fence_init();
+    }
+    __syncthreads();
+
+    if (nsteps > 0) {
+        if (w < 0) {
+            // ------------------------------------------------------------------ producer: one thread feeds the rings
+            sw_regs_producer();
+            if (w == -SW_PW && lane == 0) {
+                int slot = 0, round = 0;  // input ring position; round counts completed trips through the ring
+                int t = 0;                // operand boxes issued
+                auto issue_operands = [&](int s, int lp) {
+                    if (NF > 0 && lp >= P0 && lp < P1) {
+                        const int fs = t & 1;
+                        if (t >= 2) sw_bar_wait(&sm.fempty[fs], ((t >> 1) - 1) & 1);
+                        const int nb = NF == 1 ? 1 : (a.have_d ? 3 : 2);
+                        sw_bar_expect_tx(&sm.ffull[fs], (unsigned)(nb * SW_OP_BOX * 8));
+                        sw_tma_3d(&sm.fz[fs][0][0], &tmR, 32 * s, Y0, 3 * lp, &sm.ffull[fs]);
+                        if (NF == 3) {
+                            sw_tma_3d(&sm.fz[fs][1 % NFS][0], &tmDinv, 32 * s, Y0, 3 * lp, &sm.ffull[fs]);
+                            if (a.have_d) sw_tma_3d(&sm.fz[fs][2 % NFS][0], &tmD, 32 * s, Y0, 3 * lp, &sm.ffull[fs]);
+                        }
+                        ++t;
+                    }
+                };
+                for (int s = 0; s < nseg; ++s) {
+                    for (int j = 0; j <= nsteps; ++j) {
+                        if (round > 0) sw_bar_wait(&sm.empty[slot], (round - 1) & 1);
+                        sw_bar_expect_tx(&sm.full[slot], (unsigned)((SW_IN_BOX + (j >= 1 ? SW_E_BOX : 0)) * 8));
+                        sw_tma_3d(&sm.in[slot][0], &tmU, 32 * s, Y0, 3 * (pl0 + j), &sm.full[slot]);
+                        if (j >= 1) sw_tma_3d(&sm.E[slot][0], &tmE, 32 * s, Y0, Lstart + j - 1, &sm.full[slot]);
+                        if (++slot == RING) {
+                            slot = 0;
+                            ++round;
+                        }
+                        if (j >= 1) issue_operands(s, pl0 + j - 1);  // operands of the plane that step j - 1 completes
+                    }
+                    issue_operands(s, pl0 + nsteps);  // ... and of the plane the epilogue completes
+                }
+            }
+        } else {
+            // ------------------------------------------------------------------ consumers: warp w = cell rows Y0 + 2w, Y0 + 2w + 1
+            sw_regs_consumer();
+            int slot = 0, par = 0;      // input ring position and the parity its full barrier completes next
+            int pslot = 0, ppar = 0;    // slot / parity of the previous plane (released after that plane's store)
+            int t = 0;                  // operand boxes consumed
+            const int ey0 = Y0 + 2 * w;  // node row of my lower cell's low corner; I store rows ey0 and ey0 + 1
+            // thread-invariant values, computed once and pinned (the compiler would rematerialise them from %tid at every use)
+            int row_ok0 = (w >= 1 && ey0 <= g.ny) ? 1 : 0;  // row 0 of a tile belongs to the tile below
+            int row_ok1 = (ey0 + 1 <= g.ny) ? 1 : 0;
+            int is_top = w == SW_NW - 1 ? 1 : 0, is_bottom = w == 0 ? 1 : 0;
+            int thr_box = (2 * w) * SW_BOXZ + lane;   // my lower node inside an input / operand box plane
+            int thr_e = (2 * w) * 32 + lane;          // my lower cell inside a modulus box
+            SW_PIN32(row_ok0);
+            SW_PIN32(row_ok1);
+            SW_PIN32(is_top);
+            SW_PIN32(is_bottom);
+            SW_PIN32(thr_box);
+            SW_PIN32(thr_e);
+            const double* const in_thr = &sm.in[0][0] + thr_box;
+            const double* const e_thr = &sm.E[0][0] + thr_e;
+            const double* const fz_thr = &sm.fz[0][0][0] + thr_box;
+            double* const xch_out = &sm.xch[0][w][0][0][0] + lane;                       // what I leave for the warp above
+            const double* const xch_in = &sm.xch[0][w > 0 ? w - 1 : 0][0][0][0] + lane;  // what the warp below left for me
+            constexpr int XCH_SLOT = SW_NW * 3 * 2 * 32;
+            double* const carry_thr = carry + (2 * w) * 3;
+            SwBarAddr b_full = sw_bar_addr(&sm.full[0]), b_empty = sw_bar_addr(&sm.empty[0]);
+            SwBarAddr b_ffull = sw_bar_addr(&sm.ffull[0]), b_fempty = sw_bar_addr(&sm.fempty[0]);
+            SwBarAddr b_xfull_me = sw_bar_addr(&sm.xfull[0][w]), b_xfull_lo = sw_bar_addr(&sm.xfull[0][w > 0 ? w - 1 : 0]);
+            SW_PIN32(b_full);
+            SW_PIN32(b_empty);
+            SW_PIN32(b_xfull_me);
+            SW_PIN32(b_xfull_lo);
+            long long plane8 = g.plane, row8 = g.nzp;  // element strides of a component plane / a node row
+            SW_PIN64(plane8);
+            SW_PIN64(row8);
+            long long off_pl = 0;  // element offset of (plane lp, component 0, row ey0, my column); advanced per plane
+
+            // one output plane: AA / AB = y-z mode coefficients of the contributions of my two cells to node plane lp
+            auto finish_plane = [&](const double (&AA)[3][4], const double (&AB)[3][4], int s, int lp, int ci) {
+                {
+                    // a plane outside [P0, P1) (the first one of a chunk that starts with the redundant layer) goes through the same
+                    // exchange so that the slot / parity bookkeeping stays in step with the input ring; only its stores are skipped
+                    const bool plane_ok = lp >= P0 && lp < P1;  // CTA-uniform
+                    const bool last_seg = s == nseg - 1;
+                    const bool ext = extra && last_seg && lane == 31;
+                    const bool col_ok = plane_ok && 32 * s + lane <= g.nz;
+                    const int xs = pslot, fs = t & 1;
+                    const double* uin = in_thr + pslot * SW_IN_SLOT;  // my nodes of plane lp (its slot is still held)
+                    const double* fzp = fz_thr + fs * (NFS * SW_OP_BOX);
+                    double* cr = carry_thr + ci * SW_CARRY_ROW;
+                    // store one node: r = 0 / 1 my lower / upper node row, col = 0 my column, 1 the extra column nz
+                    auto store_node = [&](int r, int c, double s_val, int col) {
+                        const long long off = off_pl + r * row8 + c * plane8 + col;
+                        const int bo = c * SW_CROWS * SW_BOXZ + r * SW_BOXZ + col;  // offset inside an operand box
+                        if (TR::SMOOTH) {
+                            const double rv = fzp[bo];
+                            const double dinv = fzp[(1 % NFS) * SW_OP_BOX + bo];
+                            const double dprev = a.have_d ? fzp[(2 % NFS) * SW_OP_BOX + bo] : 0.0;
+                            const double v = fma(a.c1, dprev, a.c2 * dinv * (rv - s_val));
+                            a.d_out[off] = v;
+                            const double znew = uin[c * SW_ROWS * SW_BOXZ + r * SW_BOXZ + col] + v;
+                            a.y[off] = znew;
+                            if (MODE == FUSE_SMOOTH_DOT) pq[0] = fma(rv, znew, pq[0]);
+                        } else if (MODE == FUSE_RESID) {
+                            a.y[off] = fzp[bo] - s_val;
+                        } else {
+                            a.y[off] = s_val;
+                            if (MODE == FUSE_DOT) pq[0] = fma(s_val, uin[c * SW_ROWS * SW_BOXZ + r * SW_BOXZ + col], pq[0]);
+                        }
+                    };
+                    // z stage of one node row: m[c][0 / 1] = z-even / z-odd coefficient (complete over y)
+                    auto z_stage_store = [&](int r, const double (&m)[3][2], bool row_ok) {
+                        double high[3], hin[3];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) {
+                            high[c] = m[c][0] + m[c][1];  // -> node column k + 1
+                            hin[c] = sw_shfl_up1(high[c]);
+                        }
+                        if (lane == 0) {  // the z-low neighbour of lane 0 is lane 31 of the previous segment (zeros in segment 0)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) hin[c] = cr[r * 3 + c];
+                        }
+                        sw_syncwarp();  // lane 0 has read the carry of the previous segment before lane 31 overwrites it
+                        if (lane == 31 && !last_seg) {
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) cr[r * 3 + c] = high[c];
+                        }
+                        if (row_ok && col_ok) {
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) store_node(r, c, (m[c][0] - m[c][1]) + hin[c], 0);
+                        }
+                        if (ext && row_ok && plane_ok) {
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) store_node(r, c, high[c], 1);
+                        }
+                    };
+                    if (NF > 0 && plane_ok) sw_bar_wait_a(sw_bar_at(b_ffull, fs), (t >> 1) & 1);
+                    // ---- y stage inside the thread: the middle node row is complete, the upper one goes to the warp above
+                    double m1[3][2];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c)
+#pragma unroll
+                        for (int bz = 0; bz < 2; ++bz) m1[c][bz] = (AA[c][2 * bz] + AA[c][2 * bz + 1]) + (AB[c][2 * bz] - AB[c][2 * bz + 1]);
+                    if (!is_top) {
+                        double* xo = xch_out + xs * XCH_SLOT;
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+#pragma unroll
+                            for (int bz = 0; bz < 2; ++bz) xo[(c * 2 + bz) * 32] = AB[c][2 * bz] + AB[c][2 * bz + 1];
+                        sw_syncwarp();
+                        if (lane == 0) sw_bar_arrive_a(sw_bar_at(b_xfull_me, xs * SW_NW));
+                    }
+                    z_stage_store(1, m1, row_ok1 != 0);
+                    // ---- lower node row: add what the warp below left for it
+                    if (!is_bottom) {
+                        sw_bar_wait_a(sw_bar_at(b_xfull_lo, xs * SW_NW), ppar);
+                        const double* xi = xch_in + xs * XCH_SLOT;
+                        double m0[3][2];
+#pragma unroll
+                        for (int c = 0; c < 3; ++c)
+#pragma unroll
+                            for (int bz = 0; bz < 2; ++bz) m0[c][bz] = (AA[c][2 * bz] - AA[c][2 * bz + 1]) + xi[(c * 2 + bz) * 32];
+                        z_stage_store(0, m0, row_ok0 != 0);
+                    }
+                    if (NF > 0 && plane_ok) {
+                        sw_syncwarp();
+                        if (lane == 0) sw_bar_arrive_a(sw_bar_at(b_fempty, fs));
+                        ++t;
+                    }
+                }
+                off_pl += 3 * plane8;
+            };
+            auto advance_ring = [&]() {
+                pslot = slot;
+                ppar = par;
+                if (++slot == RING) {
+                    slot = 0;
+                    par ^= 1;
+                }
+            };
+            auto release = [&](int sl) {
+                sw_syncwarp();
+                if (lane == 0) sw_bar_arrive_a(sw_bar_at(b_empty, sl));
+            };
+            // z butterflies of my three node rows of the plane in ring slot sl
+            auto load_rows = [&](int sl, double (&zs)[3][3], double (&zd)[3][3]) {
+                const double* p = in_thr + sl * SW_IN_SLOT;
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const double u0 = p[c * SW_ROWS * SW_BOXZ + r * SW_BOXZ], u1 = p[c * SW_ROWS * SW_BOXZ + r * SW_BOXZ + 1];
+                        zs[r][c] = u1 + u0;
+                        zd[r][c] = u1 - u0;
+                    }
+            };
+            // the carry of segment 0 is zero
+            for (int i = w * 32 + lane; i < (nsteps + 1) * SW_CARRY_ROW; i += 32 * SW_NW) carry[i] = 0.0;
+            sw_consumer_barrier();  // consumer warps only
+
+            double GA[3][4], GB[3][4];  // contributions of my two cells to the NEXT node plane (x-high half)
+            int lp = pl0;
+            int seg = 0;
+            // one x step: FpX = modes of the previous plane (input), FnX = modes of the new plane (output)
+            auto step = [&](const double (&FpA)[3][4], const double (&FpB)[3][4], double (&FnA)[3][4], double (&FnB)[3][4], int i) {
+                sw_bar_wait_a(sw_bar_at(b_full, slot), par);
+                double zs[3][3], zd[3][3];
+                load_rows(slot, zs, zd);
+                const double EA = e_thr[slot * SW_E_BOX], EB = e_thr[slot * SW_E_BOX + 32];
+                double AA[3][4], AB[3][4];
+                sw_cell_step(a.blk, zs[0], zd[0], zs[1], zd[1], EA, FpA, FnA, GA, AA);
+                sw_cell_step(a.blk, zs[1], zd[1], zs[2], zd[2], EB, FpB, FnB, GB, AB);
+                const int held = pslot;  // plane lp: its input slot is released once the plane is stored
+                finish_plane(AA, AB, seg, lp, i);
+                release(held);
+                advance_ring();
+                ++lp;
+            };
+            for (seg = 0; seg < nseg; ++seg) {
+                // ---- first plane of the segment: only its y-z transform is needed
+                double F0A[3][4], F0B[3][4], F1A[3][4], F1B[3][4];
+                sw_bar_wait_a(sw_bar_at(b_full, slot), par);
+                {
+                    double zs[3][3], zd[3][3];
+                    load_rows(slot, zs, zd);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        F0A[c][0] = zs[1][c] + zs[0][c];
+                        F0A[c][1] = zs[1][c] - zs[0][c];
+                        F0A[c][2] = zd[1][c] + zd[0][c];
+                        F0A[c][3] = zd[1][c] - zd[0][c];
+                        F0B[c][0] = zs[2][c] + zs[1][c];
+                        F0B[c][1] = zs[2][c] - zs[1][c];
+                        F0B[c][2] = zd[2][c] + zd[1][c];
+                        F0B[c][3] = zd[2][c] - zd[1][c];
+                    }
+                }
+                advance_ring();
+#pragma unroll
+                for (int c = 0; c < 3; ++c)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) GA[c][b] = GB[c][b] = 0.0;
+                lp = pl0;
+                off_pl = (long long)pl0 * 3 * plane8 + (long long)ey0 * row8 + 32 * seg + lane;
+                int i = 0;
+#pragma unroll 1
+                for (; i + 1 < nsteps; i += 2) {
+                    step(F0A, F0B, F1A, F1B, i);
+                    step(F1A, F1B, F0A, F0B, i + 1);
+                }
+                if (i < nsteps) step(F0A, F0B, F1A, F1B, i);
+                // ---- last plane of the chunk: only the x-high half of the last cell layer
+                finish_plane(GA, GB, seg, lp, nsteps);
+                release(pslot);
+            }
+        }
+    }
+    if (TR::DOT) {
+        const unsigned int nblk = gridDim.x * gridDim.y;
+        const unsigned int bid = blockIdx.x + gridDim.x * blockIdx.y;
+        grid_reduce_idx<1, false>(pq, a.partial, a.ticket, a.dot_out, bid, nblk);
+    }
+}

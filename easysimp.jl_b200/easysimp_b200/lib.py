@@ -18,7 +18,7 @@ HEADER_PATH = PKG_DIR.parent / "include" / "easysimp_b200.h"
 
 ESIMP_FILTER_SENSITIVITY, ESIMP_FILTER_DENSITY = 0, 1
 ESIMP_CELL_TET4, ESIMP_CELL_HEX8 = 4, 8
-ESIMP_MATVEC_AUTO, ESIMP_MATVEC_DENSE_ATOMIC, ESIMP_MATVEC_FUSED, ESIMP_MATVEC_FUSED_ATOMIC, ESIMP_MATVEC_FUSED_8x32, ESIMP_MATVEC_FUSED_8x16 = range(6)
+ESIMP_MATVEC_AUTO, ESIMP_MATVEC_DENSE_ATOMIC, ESIMP_MATVEC_FUSED, ESIMP_MATVEC_FUSED_ATOMIC, ESIMP_MATVEC_FUSED_8x32, ESIMP_MATVEC_FUSED_8x16, ESIMP_MATVEC_SWEEP = range(7)
 ESIMP_WARN_PCG_MAXIT, ESIMP_WARN_OC_MAXIT = 1, 2
 
 

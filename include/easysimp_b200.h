@@ -54,6 +54,7 @@ extern "C" {
 #define ESIMP_MATVEC_FUSED_ATOMIC 3 /* same, tile perimeters combined with red.global.add.f64           */
 #define ESIMP_MATVEC_FUSED_8x32 4   /* owner-computes with 8x32 (y,z) tiles instead of 16x16            */
 #define ESIMP_MATVEC_FUSED_8x16 5   /* owner-computes with 8x16 tiles, 128-thread CTAs, 4 CTAs per SM  */
+#define ESIMP_MATVEC_SWEEP 6        /* z-sweeping TMA / mbarrier kernel (AUTO picks it where eligible)  */
 
 /* CG preconditioners */
 #define ESIMP_PRECOND_JACOBI 0 /* diagonal scaling                                                        */

@@ -12,7 +12,7 @@ from oracle import simp_oracle as o
 
 pytestmark = pytest.mark.gpu
 
-VARIANTS = {"dense_atomic": 1, "fused16x16": 2, "fused_atomic8x32": 3, "fused8x32": 4, "fused8x16": 5}
+VARIANTS = {"dense_atomic": 1, "fused16x16": 2, "fused_atomic8x32": 3, "fused8x32": 4, "fused8x16": 5, "sweep": 6}
 
 
 def relmax(a, b):
@@ -261,8 +261,9 @@ def test_host_api_simp_optimize_matches_oracle():
 
 
 # ----------------------------------------------------------------------------- multigrid-preconditioned CG
+@pytest.mark.parametrize("variant", [0, 6])  # 6: the sweep kernel (all store modes) on every level with an even nz
 @pytest.mark.parametrize("nel,right", [((32, 16, 16), (32.0, 16.0, 16.0)), ((40, 20, 20), (2.0, 1.0, 1.0)), ((24, 12, 6), (24.0, 6.0, 1.5))])
-def test_gmg_solve_matches_direct(gpu_ctx_factory, nel, right):
+def test_gmg_solve_matches_direct(gpu_ctx_factory, nel, right, variant):
     """CG with the V-cycle preconditioner reaches the same solution as the sparse direct solve, in far fewer
     iterations than Jacobi-PCG (random high-contrast modulus field, rtol 1e-10)."""
     g = o.generate_grid_hex(nel, (0, 0, 0), right)
@@ -273,7 +274,7 @@ def test_gmg_solve_matches_direct(gpu_ctx_factory, nel, right):
     f = o.apply_point_load(np.zeros(3 * g.n_nodes), dofs, sorted(o.select_nodes_by_plane(g, [right[0], 0, 0], [1, 0, 0], 1e-6)), [0.0, -1.0, 0.5])
     iters = {}
     for precond in (0, 1):
-        ctx = make_ctx(gpu_ctx_factory, g, dofs, pres, pcg_rtol=1e-10, pcg_check_every=10, precond=precond)
+        ctx = make_ctx(gpu_ctx_factory, g, dofs, pres, pcg_rtol=1e-10, pcg_check_every=10, precond=precond, matvec_variant=variant)
         ctx.set_load(f)
         ctx.set_density(rho)
         u, iters[precond], relres, st = ctx.solve()

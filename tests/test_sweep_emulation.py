@@ -1,0 +1,125 @@
+"""CPU execution of the z-sweeping TMA / mbarrier operator kernel (csrc/sweep_kernel.cuh, the source nvcc compiles into the
+product library): csrc/selftest_kernel_host.cpp runs every thread of a block as a host thread and emulates mbarriers
+(pending arrivals, transaction bytes, phase parity), 3-D TMA boxes with out-of-bounds zero fill, warp shuffles and warp
+barriers.  Every store mode is held against the oracle's assembled operator on grids that cross y tiles (15 owned node
+rows), z segments (32 columns, incl. nz % 32 == 0 where lane 31 takes the last node column along) and x chunks, on the
+padded node-row pitch the library uses, on x slabs, and under two TMA models: boxes land at issue, or a DMA thread
+delivers them later (a read before the mbarrier wait would then see stale data)."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from test_kernel_emulation import DOT, PLAIN, RESID, SMOOTH, SMOOTH_DOT, Problem, ptr, relmax
+
+ROOT = Path(__file__).resolve().parents[1]
+D = C.POINTER(C.c_double)
+
+
+@pytest.fixture(scope="module", params=["tma_lands_at_issue", "tma_lands_later"])
+def emu(request):
+    path = ROOT / "easysimp.jl_b200" / "libesimp_kernel_emu.so"
+    assert path.exists(), "run __graft_entry__.build() first"
+    lib = C.CDLL(str(path))
+    lib.emu_sweep.argtypes = [C.c_int] * 14 + [D] * 6 + [C.c_double, C.c_double, D, D]
+    lib.emu_set_deferred_tma(int(request.param == "tma_lands_later"))
+    return lib
+
+
+def pitch(nz):
+    return (nz + 1 + 3) & ~3
+
+
+def pad_rows(v_dev, nel, npx=None):
+    """[plane][c][y][z] with pitch nz + 1 -> the same with the library's padded pitch (pads = 0)"""
+    nx, ny, nz = nel
+    npx = nx + 1 if npx is None else npx
+    a = v_dev.reshape(npx, 3, ny + 1, nz + 1)
+    out = np.zeros((npx, 3, ny + 1, pitch(nz)))
+    out[..., :nz + 1] = a
+    return out.ravel()
+
+
+def unpad_rows(v_pad, nel, npx=None):
+    nx, ny, nz = nel
+    npx = nx + 1 if npx is None else npx
+    a = v_pad.reshape(npx, 3, ny + 1, pitch(nz))
+    return np.ascontiguousarray(a[..., :nz + 1]).ravel(), a[..., nz + 1:]
+
+
+def run(emu, p, mode, u, chunk=0, r=None, dinv=None, d=None, c1=0.0, c2=0.0):
+    nx, ny, nz = p.nel
+    y = np.full(3 * (nx + 1) * (ny + 1) * pitch(nz), np.nan)
+    dot = np.zeros(1)
+    dv = [None if a is None else pad_rows(p.to_dev(a), p.nel) for a in (r, dinv, d)]
+    st = emu.emu_sweep(mode, nx, ny, nz, pitch(nz), 0, nx + 1, 0, nx, 0, nx + 1, 0, nx, chunk, ptr(p.B.ravel()), ptr(p.cells_dev(p.E)),
+                       ptr(pad_rows(p.to_dev(u), p.nel)), ptr(dv[0]), ptr(dv[1]), ptr(dv[2]), c1, c2, ptr(y), ptr(dot))
+    assert st == 0
+    yv, ypad = unpad_rows(y, p.nel)
+    assert np.isnan(ypad).all()  # the pad entries of a node row are never written
+    dn = None if dv[2] is None else p.from_dev(unpad_rows(dv[2], p.nel)[0])
+    return p.from_dev(yv), dn, float(dot[0])
+
+
+# y tiles own 15 node rows, z segments hold 32 columns: (5, 18, 40) needs 2 tiles, 2 segments; (3, 33, 64) 3 tiles and the
+# extra-column path (nz % 32 == 0); (4, 6, 32) one segment with the extra column; (13, 7, 5) a single partial segment
+GRIDS = [((13, 7, 5), (13.0, 3.5, 1.25), 0), ((5, 18, 40), (5.0, 18.0, 40.0), 0), ((5, 18, 40), (5.0, 9.0, 10.0), 2),
+         ((3, 33, 64), (3.0, 33.0, 64.0), 0), ((4, 6, 32), (4.0, 6.0, 32.0), 3), ((1, 1, 1), (1.0, 1.0, 1.0), 0)]
+
+
+@pytest.mark.parametrize("nel,right,chunk", GRIDS)
+def test_plain_and_dot_modes_match_the_assembled_operator(emu, nel, right, chunk):
+    p = Problem(nel, right)
+    u = p.rng.standard_normal(p.nd)
+    want = p.A(u)
+    y, _, _ = run(emu, p, PLAIN, u, chunk=chunk)
+    assert not np.isnan(y).any() and relmax(y, want) < 2e-13
+    y2, _, dot = run(emu, p, DOT, u, chunk=chunk)
+    assert np.array_equal(y, y2) and abs(dot - u @ want) < 1e-11 * abs(u @ want)
+
+
+@pytest.mark.parametrize("nel,right,chunk", GRIDS[:4])
+def test_smoother_and_residual_modes(emu, nel, right, chunk):
+    p = Problem(nel, right, seed=1)
+    z, r, d = (p.rng.standard_normal(p.nd) for _ in range(3))
+    dinv = 1.0 / (0.5 + p.rng.random(p.nd))
+    Az = p.A(z)
+    c1, c2 = 0.37, 0.81
+    v = c1 * d + c2 * dinv * (r - Az)
+    y, dnew, _ = run(emu, p, SMOOTH, z, chunk=chunk, r=r, dinv=dinv, d=d, c1=c1, c2=c2)
+    assert relmax(y, z + v) < 1e-12 and relmax(dnew, v) < 1e-12
+    y2, dnew2, dot = run(emu, p, SMOOTH_DOT, z, chunk=chunk, r=r, dinv=dinv, d=d, c1=c1, c2=c2)
+    assert np.array_equal(y2, y) and abs(dot - r @ (z + v)) < 1e-10 * np.abs(r * (z + v)).sum()
+    v0 = c2 * dinv * (r - Az)  # c1 = 0 restarts the recurrence: d is not read at all (NaN in, finite out)
+    y, dnew, _ = run(emu, p, SMOOTH, z, chunk=chunk, r=r, dinv=dinv, d=np.full(p.nd, np.nan), c1=0.0, c2=c2)
+    assert relmax(y, z + v0) < 1e-12 and relmax(dnew, v0) < 1e-12
+    y, _, _ = run(emu, p, RESID, z, chunk=chunk, r=r)
+    assert relmax(y, r - Az) < 1e-12
+
+
+@pytest.mark.parametrize("nranks,halo_e,chunk", [(2, 1, 0), (3, 2, 2)])
+def test_x_slab_partition_reproduces_the_global_operator(emu, nranks, halo_e, chunk):
+    import easysimp_b200.partition as part
+
+    p = Problem((9, 17, 34), (9.0, 17.0, 34.0), seed=4)
+    nx, ny, nz = p.nel
+    u = p.rng.standard_normal(p.nd)
+    want = p.to_dev(p.A(u)).reshape(nx + 1, -1)
+    udev, Edev = p.to_dev(u).reshape(nx + 1, -1), p.cells_dev(p.E).reshape(nx, -1)
+    covered = np.zeros(nx + 1, dtype=int)
+    for r in range(nranks):
+        sl = part.slab_partition(nx, r, nranks, halo_e)
+        u_loc = pad_rows(np.ascontiguousarray(udev[sl.gp0:sl.gp0 + sl.npx]).ravel(), p.nel, sl.npx)
+        E_loc = np.ascontiguousarray(Edev[sl.ge0:sl.ge0 + sl.nex]).ravel()
+        y_loc = np.full(u_loc.size, np.nan)
+        assert emu.emu_sweep(PLAIN, nx, ny, nz, pitch(nz), sl.gp0, sl.npx, sl.ge0, sl.nex, sl.own_p0, sl.own_p1, sl.mv_e0, sl.mv_e1, chunk,
+                             ptr(p.B.ravel()), ptr(E_loc), ptr(u_loc), None, None, None, 0.0, 0.0, ptr(y_loc), None) == 0
+        y_loc = unpad_rows(y_loc, p.nel, sl.npx)[0].reshape(sl.npx, -1)
+        own = slice(sl.own_p0, sl.own_p1)
+        assert relmax(y_loc[own], want[sl.gp0 + sl.own_p0:sl.gp0 + sl.own_p1]) < 2e-13
+        ghost = np.ones(sl.npx, dtype=bool)
+        ghost[own] = False
+        assert np.isnan(y_loc[ghost]).all()
+        covered[sl.gp0 + sl.own_p0:sl.gp0 + sl.own_p1] += 1
+    assert (covered == 1).all()
