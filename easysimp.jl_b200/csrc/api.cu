@@ -800,4 +800,45 @@ int esimp_bench_matvec(esimp_ctx* ctx, int reps, double* ms_avg, double* bytes_p
     return ESIMP_OK;
 }
 
+int esimp_bench_operator_mode(esimp_ctx* ctx, int mode, int reps, double* ms_avg, double* bytes_per_apply) {
+    CHECK_CTX();
+    NEED(ctx->structured && ctx->density_set, "structured grid and esimp_set_density first");
+    if (reps < 1 || mode < 0 || mode > 4) return esimp_fail(ctx, ESIMP_ERR_ARG, "bad mode / reps");
+    ESIMP_CUDA(cudaMemcpyAsync(ctx->d_p, ctx->d_f, sizeof(double) * ctx->ndof_loc, cudaMemcpyDeviceToDevice, ctx->stream));
+    {
+        const double m = ctx->diag_value;
+        ctx->diag_value = 0.0;
+        int s = vec_fixup_dirichlet(ctx, ctx->d_p, ctx->d_p);  // operator input must vanish on prescribed dofs
+        ctx->diag_value = m;
+        ESIMP_TRY(s);
+    }
+    ESIMP_CUDA(cudaMemcpyAsync(ctx->d_r, ctx->d_p, sizeof(double) * ctx->ndof_loc, cudaMemcpyDeviceToDevice, ctx->stream));
+    ESIMP_CUDA(cudaMemsetAsync(ctx->d_u, 0, sizeof(double) * ctx->ndof_loc, ctx->stream));
+    const OpView vw = fine_view(ctx);
+    auto run = [&]() -> int {
+        switch (mode) {
+            case 0: return hex8_matvec_view(ctx, vw, ctx->d_p, ctx->d_q, ctx->prm.matvec_variant, -1);
+            case 1: return hex8_matvec_view(ctx, vw, ctx->d_p, ctx->d_q, ctx->prm.matvec_variant, SC_PQ);
+            case 2: return hex8_smooth_view(ctx, vw, ctx->d_p, ctx->d_q, ctx->d_r, ctx->d_dinv, ctx->d_u, 0.3, 0.7, -1);
+            case 3: return hex8_resid_view(ctx, vw, ctx->d_p, ctx->d_q, ctx->d_r);
+            default: return hex8_smooth_view(ctx, vw, ctx->d_p, ctx->d_q, ctx->d_r, ctx->d_dinv, ctx->d_u, 0.3, 0.7, SC_PQ);
+        }
+    };
+    ESIMP_TRY(run());  // warm-up
+    cudaEventRecord(ctx->ev[0], ctx->stream);
+    for (int i = 0; i < reps; ++i) ESIMP_TRY(run());
+    cudaEventRecord(ctx->ev[1], ctx->stream);
+    ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    if (ms_avg) *ms_avg = ms / reps;
+    if (bytes_per_apply) {
+        const double dofs = 3.0 * (ctx->own_p1 - ctx->own_p0) * (double)(ctx->g.ny + 1) * (double)(ctx->g.nz + 1);
+        const double per_dof = mode <= 1 ? 16.0 : (mode == 3 ? 24.0 : 48.0);
+        *bytes_per_apply = per_dof * dofs + 8.0 * (double)(ctx->own_cell1 - ctx->own_cell0);
+    }
+    ESIMP_CUDA(cudaMemsetAsync(ctx->d_u, 0, sizeof(double) * ctx->ndof_loc, ctx->stream));
+    return ESIMP_OK;
+}
+
 }  // extern "C"

@@ -18,8 +18,8 @@ struct GridDev {
     int gp0;               // global x index of local node plane 0
     int ge0;               // global x index of local element layer 0
     int e2p;               // local plane of the low face of local layer le = le + e2p
-    int nzp;               // pitch of a node row in doubles: nz + 1 rounded up to a multiple of 4, so that every row starts on a
-                           // 32-byte sector and TMA boxes (16-byte strides) can address the node vectors; the pad entries of
+    int nzp;               // pitch of a node row in doubles: nz + 1 rounded up to a multiple of 8, so that every row starts on a
+                           // 64-byte DRAM atom and TMA boxes (16-byte strides) can address the node vectors; the pad entries of
                            // every node vector are zero and stay zero (no kernel writes them, flat vector kernels map 0 to 0)
     long long plane;       // (ny+1)*nzp
     long long eplane;      // ny*nz
@@ -35,7 +35,7 @@ struct GridDev {
 };
 
 // node-row pitch for nz cells per row
-ESIMP_HD int esimp_node_pitch(int nz) { return (nz + 1 + 3) & ~3; }
+ESIMP_HD int esimp_node_pitch(int nz) { return (nz + 1 + 7) & ~7; }
 
 // where a grid reduction leaves its NV results (device pointers)
 template <int NV>

@@ -302,10 +302,10 @@ bool hex8_sweep_eligible(const esimp_ctx* ctx, const OpView& vw) {
     if (v == ESIMP_MATVEC_SWEEP) return true;                // asked for by name: any size (tests)
     return g.nz >= 64 && g.ny >= 30 && vw.own_p1 - vw.own_p0 >= 8;
 }
-template <int MODE>
-static int launch_sweep(esimp_ctx* ctx, const OpView& vw, bool fine, const double* d_in, double* d_out, int dot_slot, const FuseArgs& fa) {
+template <int MODE, int RING>
+static int launch_sweep_r(esimp_ctx* ctx, const OpView& vw, bool fine, const double* d_in, double* d_out, int dot_slot, const FuseArgs& fa) {
     using TR = SweepTraits<MODE>;
-    using Smem = SweepSmem<TR::NF, TR::RING>;
+    using Smem = SweepSmem<TR::NF, RING>;
     const GridDev& g = vw.g;
     const int nplanes = vw.own_p1 - vw.own_p0;
     const int nty = (g.ny + 1 + SW_CROWS - 2) / (SW_CROWS - 1);
@@ -332,7 +332,7 @@ static int launch_sweep(esimp_ctx* ctx, const OpView& vw, bool fine, const doubl
     const int nchunk = (nplanes + chunk - 1) / chunk;
     const size_t smem = sizeof(Smem) + (size_t)(chunk + 3) * SW_CARRY_ROW * 8;
     static unsigned long long attr_devices = 0;
-    auto kern = k_matvec_sweep<MODE>;
+    auto kern = k_matvec_sweep<MODE, RING>;
     const unsigned long long dev_bit = 1ull << (ctx->device & 63);
     if (!(attr_devices & dev_bit)) {
         ESIMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
@@ -350,6 +350,8 @@ static int launch_sweep(esimp_ctx* ctx, const OpView& vw, bool fine, const doubl
     a.c1 = fa.c1;
     a.c2 = fa.c2;
     a.have_d = fa.c1 != 0.0 ? 1 : 0;
+    static const int pfd = getenv("ESIMP_SWEEP_PFD") ? atoi(getenv("ESIMP_SWEEP_PFD")) : 0;
+    a.pf_dist = pfd;
     const long long nblk = (long long)nty * nchunk;
     if (TR::DOT && nblk > ctx->partial_mv_cap) {
         cudaFree(ctx->d_partial_mv);
@@ -360,24 +362,35 @@ static int launch_sweep(esimp_ctx* ctx, const OpView& vw, bool fine, const doubl
     a.ticket = ctx->d_ticket + 2;
     a.dot_out = RedOut<1>{{ctx->d_scal + (TR::DOT ? dot_slot : 0)}};
     memcpy(a.blk.B, ctx->B, sizeof(ctx->B));
-    alignas(64) CUtensorMap tmU, tmE, tmR, tmDinv, tmD;
+    alignas(64) CUtensorMap tmU, tmE, tmOp[3], tmOpx[3];
     const cuuint64_t nz1 = g.nz + 1, ny1 = g.ny + 1, n3 = 3ull * g.NPX;
     ESIMP_TRY(make_map3(ctx, &tmU, d_in, nz1, ny1, n3, g.nzp, g.plane, SW_BOXZ, SW_ROWS, 3));
     ESIMP_TRY(make_map3(ctx, &tmE, vw.E, g.nz, g.ny, g.NEX, g.nz, g.eplane, 32, SW_CROWS, 1));
-    tmR = tmDinv = tmD = tmU;
-    if (TR::NF >= 1) ESIMP_TRY(make_map3(ctx, &tmR, fa.r, nz1, ny1, n3, g.nzp, g.plane, SW_BOXZ, SW_CROWS, 3));
-    if (TR::NF == 3) {
-        ESIMP_TRY(make_map3(ctx, &tmDinv, fa.dinv, nz1, ny1, n3, g.nzp, g.plane, SW_BOXZ, SW_CROWS, 3));
-        ESIMP_TRY(make_map3(ctx, &tmD, fa.d, nz1, ny1, n3, g.nzp, g.plane, SW_BOXZ, SW_CROWS, 3));
+    for (int b = 0; b < 3; ++b) tmOp[b] = tmOpx[b] = tmU;
+    const double* ops[3] = {fa.r, fa.dinv, fa.d};
+    for (int b = 0; b < TR::NF; ++b) {  // r | r, Dinv, d: exactly the owned nodes of a segment, and the extra column nz
+        ESIMP_TRY(make_map3(ctx, &tmOp[b], ops[b], nz1, ny1, n3, g.nzp, g.plane, 32, SW_OROWS, 3));
+        ESIMP_TRY(make_map3(ctx, &tmOpx[b], ops[b], nz1, ny1, n3, g.nzp, g.plane, 2, SW_OROWS, 3));
     }
     const bool timed = ctx->prof_on && fine && 2 * ctx->prof_n + 1 < (int)ctx->prof_ev.size();
     if (timed) ctx->prof_tag[ctx->prof_n] = MODE <= FUSE_DOT ? 0 : 1;
     if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
-    kern<<<dim3(nty, nchunk), SW_THREADS, smem, ctx->stream>>>(a, tmU, tmE, tmR, tmDinv, tmD);
+    kern<<<dim3(nty, nchunk), SW_THREADS, smem, ctx->stream>>>(a, tmU, tmE, tmOp[0], tmOp[1], tmOp[2], tmOpx[0], tmOpx[1], tmOpx[2]);
     if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n++ + 1], ctx->stream);
     ctx->launches++;
     ESIMP_CUDA(cudaGetLastError());
     return ESIMP_OK;
+}
+
+template <int MODE>
+static int launch_sweep(esimp_ctx* ctx, const OpView& vw, bool fine, const double* d_in, double* d_out, int dot_slot, const FuseArgs& fa) {
+    static const int ring = getenv("ESIMP_SWEEP_RING") ? atoi(getenv("ESIMP_SWEEP_RING")) : 0;  // tuning: depth of the input ring
+    if (SweepTraits<MODE>::NF == 0) {
+        if (ring == 4) return launch_sweep_r<MODE, 4>(ctx, vw, fine, d_in, d_out, dot_slot, fa);
+        if (ring == 6) return launch_sweep_r<MODE, 6>(ctx, vw, fine, d_in, d_out, dot_slot, fa);
+        if (ring == 7) return launch_sweep_r<MODE, 7>(ctx, vw, fine, d_in, d_out, dot_slot, fa);
+    }
+    return launch_sweep_r<MODE, SweepTraits<MODE>::RING>(ctx, vw, fine, d_in, d_out, dot_slot, fa);
 }
 
 // the FP64 operator: modulus from the view, fine grid = the context's own modulus array
@@ -432,7 +445,10 @@ int hex8_smooth_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, doubl
     fa.d = d;
     fa.c1 = c1;
     fa.c2 = c2;
-    if (hex8_sweep_eligible(ctx, vw)) {
+    // smoother modes: 48 B/dof make them memory-latency bound, where the round-1 kernel's 16 warps per SM win (r2, 512x256x256:
+    // 1.29 ms vs 1.39 ms for the sweep kernel's 8 warps).  ESIMP_SWEEP_SMOOTH=1 (or naming the variant) selects the sweep kernel.
+    static const int sweep_smooth = getenv("ESIMP_SWEEP_SMOOTH") ? atoi(getenv("ESIMP_SWEEP_SMOOTH")) : 0;
+    if ((sweep_smooth || ctx->prm.matvec_variant == ESIMP_MATVEC_SWEEP) && hex8_sweep_eligible(ctx, vw)) {
         const bool fine = vw.E == ctx->d_E;
         return dot_slot >= 0 ? launch_sweep<FUSE_SMOOTH_DOT>(ctx, vw, fine, z_in, z_out, dot_slot, fa)
                              : launch_sweep<FUSE_SMOOTH>(ctx, vw, fine, z_in, z_out, -1, fa);

@@ -185,6 +185,7 @@ inline void sw_tma_3d(void* dst, const SwTensorMap* tm, int c0, int c1, int c2, 
         g_tma_queue.push_back(j);
     }
 }
+inline void sw_tma_prefetch_3d(const SwTensorMap*, int, int, int) {}
 // warp-level primitives: one std::barrier and one exchange row per warp of the block
 static std::vector<std::unique_ptr<std::barrier<>>> g_warp_barrier;
 static double g_shfl_row[64][32];
@@ -515,8 +516,9 @@ int emu_sweep(int mode, int nx, int ny, int nz, int nzp, int gp0, int npx, int g
         t.box[2] = 3;
         return t;
     };
-    SwTensorMap tmU = node_map(u, SW_BOXZ, SW_ROWS), tmR = node_map(r, SW_BOXZ, SW_CROWS), tmDinv = node_map(dinv, SW_BOXZ, SW_CROWS),
-                tmD = node_map(d, SW_BOXZ, SW_CROWS), tmE;
+    SwTensorMap tmU = node_map(u, SW_BOXZ, SW_ROWS), tmR = node_map(r, 32, SW_OROWS), tmDinv = node_map(dinv, 32, SW_OROWS),
+                tmD = node_map(d, 32, SW_OROWS), tmRx = node_map(r, 2, SW_OROWS), tmDinvx = node_map(dinv, 2, SW_OROWS),
+                tmDx = node_map(d, 2, SW_OROWS), tmE;
     tmE.base = E;
     tmE.dim[0] = nz;
     tmE.dim[1] = ny;
@@ -567,11 +569,11 @@ int emu_sweep(int mode, int nx, int ny, int nz, int nzp, int gp0, int npx, int g
                 threads.emplace_back([&, t] {
                     threadIdx = EmuDim3{(unsigned)t, 0, 0};
                     switch (mode) {
-                        case FUSE_PLAIN: k_matvec_sweep<FUSE_PLAIN>(a, tmU, tmE, tmR, tmDinv, tmD); break;
-                        case FUSE_DOT: k_matvec_sweep<FUSE_DOT>(a, tmU, tmE, tmR, tmDinv, tmD); break;
-                        case FUSE_SMOOTH: k_matvec_sweep<FUSE_SMOOTH>(a, tmU, tmE, tmR, tmDinv, tmD); break;
-                        case FUSE_RESID: k_matvec_sweep<FUSE_RESID>(a, tmU, tmE, tmR, tmDinv, tmD); break;
-                        case FUSE_SMOOTH_DOT: k_matvec_sweep<FUSE_SMOOTH_DOT>(a, tmU, tmE, tmR, tmDinv, tmD); break;
+                        case FUSE_PLAIN: k_matvec_sweep<FUSE_PLAIN, SweepTraits<FUSE_PLAIN>::RING>(a, tmU, tmE, tmR, tmDinv, tmD, tmRx, tmDinvx, tmDx); break;
+                        case FUSE_DOT: k_matvec_sweep<FUSE_DOT, SweepTraits<FUSE_DOT>::RING>(a, tmU, tmE, tmR, tmDinv, tmD, tmRx, tmDinvx, tmDx); break;
+                        case FUSE_SMOOTH: k_matvec_sweep<FUSE_SMOOTH, SweepTraits<FUSE_SMOOTH>::RING>(a, tmU, tmE, tmR, tmDinv, tmD, tmRx, tmDinvx, tmDx); break;
+                        case FUSE_RESID: k_matvec_sweep<FUSE_RESID, SweepTraits<FUSE_RESID>::RING>(a, tmU, tmE, tmR, tmDinv, tmD, tmRx, tmDinvx, tmDx); break;
+                        case FUSE_SMOOTH_DOT: k_matvec_sweep<FUSE_SMOOTH_DOT, SweepTraits<FUSE_SMOOTH_DOT>::RING>(a, tmU, tmE, tmR, tmDinv, tmD, tmRx, tmDinvx, tmDx); break;
                     }
                 });
             for (auto& th : threads) th.join();

@@ -29,7 +29,10 @@ constexpr int SW_PW = 4;                // producer warps: one whole warpgroup (
 constexpr int SW_THREADS = 32 * (SW_NW + SW_PW);
 constexpr int SW_IN_BOX = 3 * SW_ROWS * SW_BOXZ;                 // doubles in an input box {34, 17, 3}
 constexpr int SW_IN_SLOT = (SW_IN_BOX * 8 + 127) / 128 * 16;     // slot pitch in doubles: TMA destinations are 128-byte aligned
-constexpr int SW_OP_BOX = 3 * SW_CROWS * SW_BOXZ;                // operand box {34, 16, 3}: 13056 B = 102 * 128
+constexpr int SW_OROWS = SW_CROWS - 1;                           // node rows a tile owns = rows of an operand box
+constexpr int SW_OP_BOX = 3 * SW_OROWS * 32;                     // operand box {32, 15, 3}: exactly the owned nodes of a segment, 11520 B = 90 * 128
+constexpr int SW_OPX_BOX = 3 * SW_OROWS * 2;                     // ... and {2, 15, 3} for the extra node column nz of the last segment (720 B)
+constexpr int SW_OPX_SLOT = 96;                                  // its slot pitch in doubles (768 B = 6 * 128)
 constexpr int SW_E_BOX = SW_CROWS * 32;                          // modulus box {32, 16, 1}
 
 struct SweepBlocks {
@@ -72,6 +75,11 @@ __device__ __forceinline__ void sw_tma_3d(void* dst, const SwTensorMap* tm, int 
                  "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(sw_smem(bar))
                  : "memory");
 }
+// pull a box into L2 only (no shared-memory destination, no barrier): issued a few planes ahead of the real load, so that the
+// DRAM latency under load is not bounded by the depth of the shared-memory ring
+__device__ __forceinline__ void sw_tma_prefetch_3d(const SwTensorMap* tm, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tm), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
 __device__ __forceinline__ double sw_shfl_up1(double v) {
     const int lo = __shfl_up_sync(0xffffffffu, __double2loint(v), 1), hi = __shfl_up_sync(0xffffffffu, __double2hiint(v), 1);
     return __hiloint2double(hi, lo);
@@ -89,14 +97,20 @@ __device__ __forceinline__ void sw_consumer_barrier() { asm volatile("bar.sync 1
 
 template <int NF, int RING>
 struct SweepSmem {
+    // XE: 2-slot y exchange with an explicit empty barrier, the shared memory it frees spent on a third operand slot.  Measured
+    // at 512x256x256 (r2): smoother 1.39 -> 1.35 ms but residual 0.73 -> 0.80 ms (shorter x chunks, one more wait per plane), so
+    // it stays off: the exchange ring is indexed like the input ring and needs no empty barrier, operands are double-buffered
+    static constexpr bool XE = false;
+    static constexpr int XN = XE ? 2 : RING, FN = NF > 0 ? (XE ? 3 : 2) : 1;
     alignas(128) double in[RING][SW_IN_SLOT];                             // node-plane boxes [c][17 rows][34]
     alignas(128) double E[RING][SW_E_BOX];                                // modulus boxes [16 rows][32]
-    alignas(128) double fz[NF > 0 ? 2 : 1][NF > 0 ? NF : 1][SW_OP_BOX];   // r | r, Dinv, d boxes [c][16 rows][34]
+    alignas(128) double fz[FN][NF > 0 ? NF : 1][NF > 0 ? SW_OP_BOX : 16];     // r | r, Dinv, d boxes [c][15 owned rows][32]
+    alignas(128) double fzx[FN][NF > 0 ? NF : 1][NF > 0 ? SW_OPX_SLOT : 16];  // the same for node column nz: [c][15 rows][2]
     // y-high mode coefficients (bz = 0, 1) of warp w's upper cell for node row 2w + 2 (warp w + 1).  One slot per input-ring
     // slot, indexed like the plane it belongs to: warp w + 1 has read the slot before it releases that plane's input slot, and
     // warp w cannot be RING planes ahead of a plane that is not released, so no "empty" barrier is needed for this exchange
-    double xch[RING][SW_NW][3][2][32];
-    SwBar full[RING], empty[RING], ffull[2], fempty[2], xfull[RING][SW_NW];
+    double xch[XN][SW_NW][3][2][32];
+    SwBar full[RING], empty[RING], ffull[FN], fempty[FN], xfull[XN][SW_NW], xempty[XN][SW_NW];
 };
 // the carry rows follow the struct: carry[ci][row][3] = z-high face sums of lane 31 (per node row, component), read by
 // lane 0 one segment later; row ci = 0 .. nsteps (output planes of the chunk)
@@ -117,6 +131,7 @@ struct SweepArgs {
     double* d_out;    // FUSE_SMOOTH: the Chebyshev direction is updated in place (read through the d tensor map)
     double c1, c2;
     int have_d;       // FUSE_SMOOTH: c1 != 0 (the first step of a sweep has no previous direction)
+    int pf_dist;      // producer: planes by which the L2 prefetch runs ahead of the shared-memory loads (0 = none)
     double* partial;
     unsigned int* ticket;
     RedOut<1> dot_out;
@@ -179,14 +194,16 @@ __device__ __forceinline__ void sw_cell_step(const SweepBlocks& blk, const doubl
     }
 }
 
-template <int MODE>
+template <int MODE, int RING>
 __global__ void __launch_bounds__(SW_THREADS, 1)
     k_matvec_sweep(const __grid_constant__ SweepArgs a, const __grid_constant__ SwTensorMap tmU, const __grid_constant__ SwTensorMap tmE,
-                   const __grid_constant__ SwTensorMap tmR, const __grid_constant__ SwTensorMap tmDinv, const __grid_constant__ SwTensorMap tmD) {
+                   const __grid_constant__ SwTensorMap tmR, const __grid_constant__ SwTensorMap tmDinv, const __grid_constant__ SwTensorMap tmD,
+                   const __grid_constant__ SwTensorMap tmRx, const __grid_constant__ SwTensorMap tmDinvx, const __grid_constant__ SwTensorMap tmDx) {
     using TR = SweepTraits<MODE>;
-    constexpr int NF = TR::NF, RING = TR::RING, NFS = NF > 0 ? NF : 1;
+    constexpr int NF = TR::NF, NFS = NF > 0 ? NF : 1;
     SW_SMEM_DECL;
-    SweepSmem<NF, RING>& sm = *reinterpret_cast<SweepSmem<NF, RING>*>(sw_smem_raw);
+    using SM = SweepSmem<NF, RING>;
+    SM& sm = *reinterpret_cast<SM*>(sw_smem_raw);
     double* const carry = reinterpret_cast<double*>(sw_smem_raw + sizeof(SweepSmem<NF, RING>));
     const GridDev& g = a.g;
     int w = (int)(threadIdx.x >> 5) - SW_PW, lane = threadIdx.x & 31;  // w < 0: producer warpgroup, w = 0 .. 7: consumer warps
@@ -204,9 +221,13 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
         for (int s = 0; s < RING; ++s) {
             sw_bar_init(&sm.full[s], 1);
             sw_bar_init(&sm.empty[s], SW_NW);
-            for (int r = 0; r < SW_NW; ++r) sw_bar_init(&sm.xfull[s][r], 1);
         }
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < SM::XN; ++s)
+            for (int r = 0; r < SW_NW; ++r) {
+                sw_bar_init(&sm.xfull[s][r], 1);
+                sw_bar_init(&sm.xempty[s][r], 1);
+            }
+        for (int s = 0; s < SM::FN; ++s) {
             sw_bar_init(&sm.ffull[s], 1);
             sw_bar_init(&sm.fempty[s], SW_NW);
         }
@@ -223,20 +244,32 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
                 int t = 0;                // operand boxes issued
                 auto issue_operands = [&](int s, int lp) {
                     if (NF > 0 && lp >= P0 && lp < P1) {
-                        const int fs = t & 1;
-                        if (t >= 2) sw_bar_wait(&sm.fempty[fs], ((t >> 1) - 1) & 1);
+                        const int fs = t % SM::FN;
+                        if (t >= SM::FN) sw_bar_wait(&sm.fempty[fs], ((t / SM::FN) - 1) & 1);
                         const int nb = NF == 1 ? 1 : (a.have_d ? 3 : 2);
-                        sw_bar_expect_tx(&sm.ffull[fs], (unsigned)(nb * SW_OP_BOX * 8));
-                        sw_tma_3d(&sm.fz[fs][0][0], &tmR, 32 * s, Y0, 3 * lp, &sm.ffull[fs]);
-                        if (NF == 3) {
-                            sw_tma_3d(&sm.fz[fs][1 % NFS][0], &tmDinv, 32 * s, Y0, 3 * lp, &sm.ffull[fs]);
-                            if (a.have_d) sw_tma_3d(&sm.fz[fs][2 % NFS][0], &tmD, 32 * s, Y0, 3 * lp, &sm.ffull[fs]);
+                        const bool xcol = extra && s == nseg - 1;  // the last segment also brings the operands of node column nz
+                        sw_bar_expect_tx(&sm.ffull[fs], (unsigned)(nb * (SW_OP_BOX + (xcol ? SW_OPX_BOX : 0)) * 8));
+                        const SwTensorMap* maps[6] = {&tmR, &tmDinv, &tmD, &tmRx, &tmDinvx, &tmDx};
+                        for (int b = 0; b < nb; ++b) {
+                            sw_tma_3d(&sm.fz[fs][b % NFS][0], maps[b], 32 * s, Y0 + 1, 3 * lp, &sm.ffull[fs]);
+                            if (xcol) sw_tma_3d(&sm.fzx[fs][b % NFS][0], maps[3 + b], g.nz, Y0 + 1, 3 * lp, &sm.ffull[fs]);
                         }
                         ++t;
                     }
                 };
+                const int per_seg = nsteps + 1, total = nseg * per_seg;
+                auto prefetch_l2 = [&](int L) {  // the L-th plane this CTA loads (segments are swept one after the other)
+                    if (L < total) {
+                        const int ps = L / per_seg, pj = L - ps * per_seg;
+                        sw_tma_prefetch_3d(&tmU, 32 * ps, Y0, 3 * (pl0 + pj));
+                        if (pj >= 1) sw_tma_prefetch_3d(&tmE, 32 * ps, Y0, Lstart + pj - 1);
+                    }
+                };
+                if (a.pf_dist > 0)
+                    for (int L = RING; L < RING + a.pf_dist; ++L) prefetch_l2(L);
                 for (int s = 0; s < nseg; ++s) {
                     for (int j = 0; j <= nsteps; ++j) {
+                        if (a.pf_dist > 0) prefetch_l2(s * per_seg + j + RING + a.pf_dist);
                         if (round > 0) sw_bar_wait(&sm.empty[slot], (round - 1) & 1);
                         sw_bar_expect_tx(&sm.full[slot], (unsigned)((SW_IN_BOX + (j >= 1 ? SW_E_BOX : 0)) * 8));
                         sw_tma_3d(&sm.in[slot][0], &tmU, 32 * s, Y0, 3 * (pl0 + j), &sm.full[slot]);
@@ -255,7 +288,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
             sw_regs_consumer();
             int slot = 0, par = 0;      // input ring position and the parity its full barrier completes next
             int pslot = 0, ppar = 0;    // slot / parity of the previous plane (released after that plane's store)
-            int t = 0;                  // operand boxes consumed
+            int t = 0, fs = 0, fpar = 0;  // operand boxes consumed; slot and parity of the next one
+            int xcount = 0;             // y exchanges done (fused modes: 2-slot exchange with an empty barrier)
             const int ey0 = Y0 + 2 * w;  // node row of my lower cell's low corner; I store rows ey0 and ey0 + 1
             // thread-invariant values, computed once and pinned (the compiler would rematerialise them from %tid at every use)
             int row_ok0 = (w >= 1 && ey0 <= g.ny) ? 1 : 0;  // row 0 of a tile belongs to the tile below
@@ -271,7 +305,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
             SW_PIN32(thr_e);
             const double* const in_thr = &sm.in[0][0] + thr_box;
             const double* const e_thr = &sm.E[0][0] + thr_e;
-            const double* const fz_thr = &sm.fz[0][0][0] + thr_box;
+            const double* const fz_thr = &sm.fz[0][0][0] + (2 * w - 1) * 32 + lane;   // box row of node row r of mine: 2w - 1 + r
+            const double* const fzx_thr = &sm.fzx[0][0][0] + (2 * w - 1) * 2;
             double* const xch_out = &sm.xch[0][w][0][0][0] + lane;                       // what I leave for the warp above
             const double* const xch_in = &sm.xch[0][w > 0 ? w - 1 : 0][0][0][0] + lane;  // what the warp below left for me
             constexpr int XCH_SLOT = SW_NW * 3 * 2 * 32;
@@ -279,6 +314,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
             SwBarAddr b_full = sw_bar_addr(&sm.full[0]), b_empty = sw_bar_addr(&sm.empty[0]);
             SwBarAddr b_ffull = sw_bar_addr(&sm.ffull[0]), b_fempty = sw_bar_addr(&sm.fempty[0]);
             SwBarAddr b_xfull_me = sw_bar_addr(&sm.xfull[0][w]), b_xfull_lo = sw_bar_addr(&sm.xfull[0][w > 0 ? w - 1 : 0]);
+            SwBarAddr b_xempty_me = sw_bar_addr(&sm.xempty[0][w]), b_xempty_lo = sw_bar_addr(&sm.xempty[0][w > 0 ? w - 1 : 0]);
             SW_PIN32(b_full);
             SW_PIN32(b_empty);
             SW_PIN32(b_xfull_me);
@@ -286,7 +322,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
             long long plane8 = g.plane, row8 = g.nzp;  // element strides of a component plane / a node row
             SW_PIN64(plane8);
             SW_PIN64(row8);
-            long long off_pl = 0;  // element offset of (plane lp, component 0, row ey0, my column); advanced per plane
+            // running pointers to (plane lp, component 0, row ey0, my column) of the result (and of the direction vector the smoother
+            // updates): advanced by one node plane per step, so a store costs two adds instead of a full index computation
+            double* yp = a.y;
+            double* dp = a.d_out;
 
             // one output plane: AA / AB = y-z mode coefficients of the contributions of my two cells to node plane lp
             auto finish_plane = [&](const double (&AA)[3][4], const double (&AB)[3][4], int s, int lp, int ci) {
@@ -297,27 +336,32 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
                     const bool last_seg = s == nseg - 1;
                     const bool ext = extra && last_seg && lane == 31;
                     const bool col_ok = plane_ok && 32 * s + lane <= g.nz;
-                    const int xs = pslot, fs = t & 1;
+                    constexpr bool XE = SM::XE;
+                    const int xs = XE ? (xcount & 1) : pslot;
+                    const int xpar = XE ? ((xcount >> 1) & 1) : ppar;
                     const double* uin = in_thr + pslot * SW_IN_SLOT;  // my nodes of plane lp (its slot is still held)
                     const double* fzp = fz_thr + fs * (NFS * SW_OP_BOX);
+                    const double* fzxp = fzx_thr + fs * (NFS * SW_OPX_SLOT);
                     double* cr = carry_thr + ci * SW_CARRY_ROW;
                     // store one node: r = 0 / 1 my lower / upper node row, col = 0 my column, 1 the extra column nz
                     auto store_node = [&](int r, int c, double s_val, int col) {
-                        const long long off = off_pl + r * row8 + c * plane8 + col;
-                        const int bo = c * SW_CROWS * SW_BOXZ + r * SW_BOXZ + col;  // offset inside an operand box
+                        const long long off = r * row8 + c * plane8 + col;
+                        // operands of this node: my own column from the {32, 15, 3} box, the extra column from the {2, 15, 3} one
+                        const double* op = col ? fzxp + c * SW_OROWS * 2 + r * 2 : fzp + c * SW_OROWS * 32 + r * 32;
+                        const int ostride = col ? SW_OPX_SLOT : SW_OP_BOX;
                         if (TR::SMOOTH) {
-                            const double rv = fzp[bo];
-                            const double dinv = fzp[(1 % NFS) * SW_OP_BOX + bo];
-                            const double dprev = a.have_d ? fzp[(2 % NFS) * SW_OP_BOX + bo] : 0.0;
+                            const double rv = op[0];
+                            const double dinv = op[(1 % NFS) * ostride];
+                            const double dprev = a.have_d ? op[(2 % NFS) * ostride] : 0.0;
                             const double v = fma(a.c1, dprev, a.c2 * dinv * (rv - s_val));
-                            a.d_out[off] = v;
+                            dp[off] = v;
                             const double znew = uin[c * SW_ROWS * SW_BOXZ + r * SW_BOXZ + col] + v;
-                            a.y[off] = znew;
+                            yp[off] = znew;
                             if (MODE == FUSE_SMOOTH_DOT) pq[0] = fma(rv, znew, pq[0]);
                         } else if (MODE == FUSE_RESID) {
-                            a.y[off] = fzp[bo] - s_val;
+                            yp[off] = op[0] - s_val;
                         } else {
-                            a.y[off] = s_val;
+                            yp[off] = s_val;
                             if (MODE == FUSE_DOT) pq[0] = fma(s_val, uin[c * SW_ROWS * SW_BOXZ + r * SW_BOXZ + col], pq[0]);
                         }
                     };
@@ -347,7 +391,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
                             for (int c = 0; c < 3; ++c) store_node(r, c, high[c], 1);
                         }
                     };
-                    if (NF > 0 && plane_ok) sw_bar_wait_a(sw_bar_at(b_ffull, fs), (t >> 1) & 1);
+                    if (NF > 0 && plane_ok) sw_bar_wait_a(sw_bar_at(b_ffull, fs), fpar);
                     // ---- y stage inside the thread: the middle node row is complete, the upper one goes to the warp above
                     double m1[3][2];
 #pragma unroll
@@ -355,6 +399,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
 #pragma unroll
                         for (int bz = 0; bz < 2; ++bz) m1[c][bz] = (AA[c][2 * bz] + AA[c][2 * bz + 1]) + (AB[c][2 * bz] - AB[c][2 * bz + 1]);
                     if (!is_top) {
+                        if (XE && xcount >= 2) sw_bar_wait_a(sw_bar_at(b_xempty_me, xs * SW_NW), ((xcount >> 1) - 1) & 1);
                         double* xo = xch_out + xs * XCH_SLOT;
 #pragma unroll
                         for (int c = 0; c < 3; ++c)
@@ -366,22 +411,32 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
                     z_stage_store(1, m1, row_ok1 != 0);
                     // ---- lower node row: add what the warp below left for it
                     if (!is_bottom) {
-                        sw_bar_wait_a(sw_bar_at(b_xfull_lo, xs * SW_NW), ppar);
+                        sw_bar_wait_a(sw_bar_at(b_xfull_lo, xs * SW_NW), xpar);
                         const double* xi = xch_in + xs * XCH_SLOT;
                         double m0[3][2];
 #pragma unroll
                         for (int c = 0; c < 3; ++c)
 #pragma unroll
                             for (int bz = 0; bz < 2; ++bz) m0[c][bz] = (AA[c][2 * bz] - AA[c][2 * bz + 1]) + xi[(c * 2 + bz) * 32];
+                        if (XE) {
+                            sw_syncwarp();
+                            if (lane == 0) sw_bar_arrive_a(sw_bar_at(b_xempty_lo, xs * SW_NW));
+                        }
                         z_stage_store(0, m0, row_ok0 != 0);
                     }
                     if (NF > 0 && plane_ok) {
                         sw_syncwarp();
                         if (lane == 0) sw_bar_arrive_a(sw_bar_at(b_fempty, fs));
                         ++t;
+                        if (++fs == SM::FN) {
+                            fs = 0;
+                            fpar ^= 1;
+                        }
                     }
+                    ++xcount;
                 }
-                off_pl += 3 * plane8;
+                yp += 3 * plane8;
+                if (TR::SMOOTH) dp += 3 * plane8;
             };
             auto advance_ring = [&]() {
                 pslot = slot;
@@ -454,7 +509,11 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
 #pragma unroll
                     for (int b = 0; b < 4; ++b) GA[c][b] = GB[c][b] = 0.0;
                 lp = pl0;
-                off_pl = (long long)pl0 * 3 * plane8 + (long long)ey0 * row8 + 32 * seg + lane;
+                {
+                    const long long off0 = (long long)pl0 * 3 * plane8 + (long long)ey0 * row8 + 32 * seg + lane;
+                    yp = a.y + off0;
+                    if (TR::SMOOTH) dp = a.d_out + off0;
+                }
                 int i = 0;
 #pragma unroll 1
                 for (; i + 1 < nsteps; i += 2) {

@@ -83,6 +83,7 @@ _SIGNATURES = {
     "esimp_n_dofs": (C.c_int64, [_P]),
     "esimp_n_cells": (C.c_int64, [_P]),
     "esimp_bench_matvec": (C.c_int, [_P, C.c_int, _D, _D]),
+    "esimp_bench_operator_mode": (C.c_int, [_P, C.c_int, C.c_int, _D, _D]),
     "esimp_launch_count": (C.c_int64, [_P]),
     "esimp_set_design": (C.c_int, [_P, _D]),
     "esimp_profile_enable": (C.c_int, [_P, C.c_int]),
@@ -370,6 +371,12 @@ class Context:
         n = C.c_int64(0)
         self._chk(self.lib.esimp_profile_operator_all(self._h, C.byref(ms), C.byref(n)), "esimp_profile_operator_all")
         return ms.value, n.value
+
+    def bench_operator_mode(self, mode, reps):
+        ms = C.c_double(0)
+        by = C.c_double(0)
+        self._chk(self.lib.esimp_bench_operator_mode(self._h, mode, reps, C.byref(ms), C.byref(by)), "esimp_bench_operator_mode")
+        return ms.value, by.value
 
     def bench_matvec(self, reps):
         ms = C.c_double(0)

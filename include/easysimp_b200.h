@@ -211,6 +211,10 @@ int64_t esimp_n_cells(const esimp_ctx* ctx);
 /* `reps` operator applies on device-resident vectors; ms_avg = mean launch-to-launch time.
  * bytes_per_apply = algorithmic bytes (16*n_dof + 8*n_cell). */
 int esimp_bench_matvec(esimp_ctx* ctx, int reps, double* ms_avg, double* bytes_per_apply);
+/* the same for one store mode of the structured operator kernel on the fine grid: 0 plain, 1 plain + <u,y>, 2 multigrid
+ * smoother step fused into the store (reads r, Dinv, d; writes z', d), 3 residual r - A z, 4 smoother step + <r,z'>.
+ * bytes_per_apply = 16 B/dof + 8 B/cell for modes 0-1, 48 B/dof + 8 B/cell for 2 and 4, 24 B/dof + 8 B/cell for 3. */
+int esimp_bench_operator_mode(esimp_ctx* ctx, int mode, int reps, double* ms_avg, double* bytes_per_apply);
 /* in-region timing: while enabled, every launch of the structured operator kernel is bracketed by
  * CUDA events on the context's stream; esimp_profile_matvec returns the summed kernel time, the number
  * of timed launches and the algorithmic bytes one launch moves on this rank. */

@@ -1,0 +1,6 @@
+#!/bin/bash
+set -u
+mkdir -p gpurun_out
+timeout 200 python scripts/bench_operator_modes.py 512 256 256 6 2 0,2 > gpurun_out/plain_for_ncu.log 2>&1 &&
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_matvec_sweep -c 6 -f -o gpurun_out/prof_r2_sweep_v2 python scripts/bench_operator_modes.py 512 256 256 6 2 0,2 > gpurun_out/ncu_r2_sweep_v2.log 2>&1
+tail -2 gpurun_out/ncu_r2_sweep_v2.log

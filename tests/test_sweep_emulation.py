@@ -28,7 +28,7 @@ def emu(request):
 
 
 def pitch(nz):
-    return (nz + 1 + 3) & ~3
+    return (nz + 1 + 7) & ~7
 
 
 def pad_rows(v_dev, nel, npx=None):
