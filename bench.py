@@ -5,12 +5,21 @@
     python bench.py --impl reference --gpus N ...            # the reference's CPU path, restated (oracle/cpu_simp.c)
     torchrun --nproc-per-node N bench.py --gpus N ...        # N > 1: one rank per GPU, x-slab partition, NCCL
 
-A "step" is ONE SIMP iteration (Optimization.jl:271-379): modulus + Jacobi diagonal, FP64 PCG solve to
-`--pcg-rtol` (warm-started), element sensitivities + energy, sensitivity filter, OC bisection, metrics.
-Workload at every N: the 512x256x256 unit-cube cantilever (33.5 M cells, 101.6 M dofs; strong scaling),
-clamped at x = 0, unit load at the tip (SURVEY 8d recipe).  `value` times esimp_iterate with all state
-resident in HBM; `e2e` times the same step driven through the C ABI with HOST buffers (design densities
-copied host->device before and device->host after every iteration, from/to pinned memory).
+A "step" is ONE SIMP iteration (Optimization.jl:271-379): modulus + Jacobi diagonal, FP64 CG solve to `--pcg-rtol`
+(warm-started), element sensitivities + energy, sensitivity filter, OC bisection, metrics.  Workload at every N: the
+512x256x256 unit-cube cantilever (33.5 M cells, 101.6 M dofs; strong scaling), clamped at x = 0, unit load at the tip
+(SURVEY 8d recipe).
+
+`value`   K iterations with all state resident in HBM, after W warm-up iterations from the uniform start design.
+`e2e`     THE SAME K iterations (the design is reset, the same W warm-up iterations run again) driven through the C ABI with
+          HOST buffers: design densities copied host->device before and device->host after every iteration (pinned memory).
+`roofline`        the operator kernel's plain / plain+dot launches, CUDA-event timed inside the step.
+`roofline_others` the same clock for the other fine-grid kernels of the step (smoother / residual modes of the operator,
+                  filter, sensitivities, OC volumes, prolongation, restriction, the fused CG vector kernels).
+`cpu_baseline`    oracle/cpu_simp.c (OpenMP port, Jacobi-PCG) on a bounded sample at the full size -- EXTRAPOLATED with the
+                  Jacobi-PCG iteration count of the same SIMP iteration window (bench_calibration.json).
+`cpu_baseline_measured`  the oracle's direct-solve path (sparse assembly + sparse LU, what the reference does with CHOLMOD)
+                  run to completion on the README cantilever 60x20x4, per phase, beside the CUDA path on the same problem.
 """
 import argparse
 import json
@@ -33,19 +42,28 @@ CALIB = ROOT / "bench_calibration.json"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c5", choices=list(WORKLOADS))
     ap.add_argument("--pcg-rtol", type=float, default=1e-8)
     ap.add_argument("--filter-radius", type=float, default=1.5)
     ap.add_argument("--volfrac", type=float, default=0.5)
     ap.add_argument("--variant", type=int, default=0)
-    ap.add_argument("--precond", default="gmg", choices=["jacobi", "gmg", "gmg32"],
-                    help="gmg32 = the V-cycle evaluated in fp32 inside the fp64 CG (opt-in, csrc/multigrid32.cu)")
+    ap.add_argument("--precond", default="gmg", choices=["jacobi", "gmg"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-measured-iters", type=int, default=3, help="SIMP iterations of the direct-solve oracle on 60x20x4 (0 = skip)")
     return ap.parse_args()
+
+
+def host_threads():
+    """threads the CPU legs use: every core this process may run on (torchrun exports OMP_NUM_THREADS=1 for nproc > 1;
+    the CPU port is told the count explicitly)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 def cantilever(nel):
@@ -112,17 +130,37 @@ def measured_peak():
         return 6650.0, "fallback"
 
 
-def cpu_sample(nel, args, pcg_iters_per_step, n_pcg=3):
-    """Bounded sample of the CPU path at full size: `n_pcg` PCG iterations + sensitivities + filter + the
-    whole OC bisection, timed with all host threads; the PCG part is scaled to `pcg_iters_per_step`."""
+# ------------------------------------------------------------------------------------------------ CPU legs
+def jacobi_pcg_iters(workload, warmup, steps):
+    """Jacobi-PCG iterations per SIMP iteration of the window [warmup, warmup + steps), measured once with the CUDA arm's own
+    Jacobi-PCG (same algorithm as the CPU port, same rtol, same design trajectory): bench_calibration.json"""
+    try:
+        c = json.load(open(CALIB))[workload]
+        hist = c.get("pcg_iters_by_simp_iteration")
+        if hist:
+            win = hist[warmup:warmup + steps]
+            if len(win) == steps:
+                return float(np.mean(win)), f"bench_calibration.json, SIMP iterations {warmup + 1}..{warmup + steps} (the timed window)", True
+            return float(np.mean(hist[-min(len(hist), steps):])), "bench_calibration.json, last calibrated iterations (window extends past the calibration)", False
+        return float(c["mean_pcg_iters_per_step"]), "bench_calibration.json (mean of its own window)", False
+    except Exception:
+        return 2000.0, "nominal (no calibration file)", False
+
+
+def cpu_sample(nel, args, pcg_iters_per_step, iters_note, n_pcg=2):
+    """Bounded sample of the CPU port at full size: `n_pcg` Jacobi-PCG iterations + sensitivities + filter + the whole OC
+    bisection, timed with all host threads; the PCG part is scaled to `pcg_iters_per_step` (an EXTRAPOLATION)."""
     from oracle import cpu_port as cp
     from oracle import simp_oracle as o
 
+    nthreads = host_threads()
+    cp.lib().cpu_set_threads(nthreads)
     nx, ny, nz = nel
     pres, f = cantilever(nel)
     fixed = np.zeros(f.size, dtype=np.uint8)
     fixed[pres] = 1
-    K0 = np.ascontiguousarray(o.hex8_ke(o.generate_grid_hex((1, 1, 1)).coords[o.generate_grid_hex((1, 1, 1)).cells[0]], *o.lame(1.0, 0.3)))
+    g1 = o.generate_grid_hex((1, 1, 1))
+    K0 = np.ascontiguousarray(o.hex8_ke(g1.coords[g1.cells[0]], *o.lame(1.0, 0.3)))
     rho = np.full(nx * ny * nz, args.volfrac)
     u = np.zeros_like(f)
     prm = dict(E0=1.0, Emin=1e-9, p=3.0, R=args.filter_radius, move=0.2, damping=0.5, volfrac=args.volfrac)
@@ -132,56 +170,145 @@ def cpu_sample(nel, args, pcg_iters_per_step, n_pcg=3):
     per_pcg = t["pcg"] / (t["pcg_iters"] + 1)
     other = t["modulus"] + t["sens"] + t["filter"] + t["oc"]
     t_step = per_pcg * pcg_iters_per_step + other
-    return {"value": 1.0 / t_step, "unit": "iter/s", "cores": cp.num_threads(), "kind": "port",
-            "sample": f"{nx}x{ny}x{nz}: {n_pcg} Jacobi-PCG iterations ({per_pcg:.3f} s each, OpenMP, dense 24x24 K_e u_e per cell) scaled to "
-                      f"{pcg_iters_per_step:.0f} PCG iterations/step (count of the same PCG at rtol {args.pcg_rtol:g}), plus one full sensitivity pass "
-                      f"({t['sens']:.2f} s), sensitivity filter ({t['filter']:.2f} s) and OC bisection ({t['oc']:.2f} s, {t['oc_steps']} steps); "
+    return {"value": 1.0 / t_step, "unit": "iter/s", "cores": cp.num_threads(), "kind": "port", "extrapolated": True,
+            "sample": f"{nx}x{ny}x{nz}: {n_pcg} Jacobi-PCG iterations measured ({per_pcg:.3f} s each, OpenMP x{cp.num_threads()}, dense 24x24 K_e u_e per cell), "
+                      f"EXTRAPOLATED to {pcg_iters_per_step:.0f} PCG iterations/step ({iters_note}; rtol {args.pcg_rtol:g}), plus one full sensitivity pass "
+                      f"({t['sens']:.2f} s), sensitivity filter ({t['filter']:.2f} s) and OC bisection ({t['oc']:.2f} s, {t['oc_steps']} steps), all measured; "
                       "the reference's own Ferrite assembly + CHOLMOD solve cannot exist at this size (K alone ~100 GB) and Julia is not installed",
-            "seconds_per_step": t_step}
+            "seconds_per_step": t_step, "seconds_measured": t["pcg"] + other}
 
 
-def calibrated_pcg_iters(workload, rtol):
+def cpu_direct_path(n_iter, threads):
+    """The oracle's restatement of the reference's CPU path (sparse assembly, apply!, sparse direct solve, sensitivities,
+    filter, OC: Optimization.jl:271-379) run to completion for `n_iter` SIMP iterations on the README cantilever 60x20x4
+    (BASELINE config 1: E0 = 1, Emin = 1e-9, nu = 0.3, vf = 0.5, r = 1.5, sensitivity filter); seconds per phase."""
+    from oracle import simp_oracle as o
+
     try:
-        c = json.load(open(CALIB))[workload]
-        return float(c["mean_pcg_iters_per_step"]), c
+        from threadpoolctl import threadpool_limits
     except Exception:
-        return 2000.0, None
+        threadpool_limits = None
+    g, dofs, f, pres = o.cantilever_problem((60, 20, 4))
+    prm = o.OptimizationParameters(volume_fraction=0.5, filter_radius=1.5 * o.estimate_element_size(g))
+    V = o.element_volumes(g)
+    Vtot = float(V.sum())
+    fc = o.create_filter_cache(g, prm.filter_radius, V)
+    k_unit = o.unit_element_matrices(g, prm.nu, prm.E0)
+    k0 = o.unit_element_matrices(g, prm.nu, 1.0)
+    dv = V / Vtot
+    rho = np.full(g.n_cells, prm.volume_fraction)
+    ph = {k: 0.0 for k in ("assembly", "apply_bc", "solve", "energy", "sensitivities", "filter", "oc")}
+    energies = []
+
+    def loop():
+        nonlocal rho
+        for _ in range(n_iter):
+            t0 = time.perf_counter()
+            E = o.simp_modulus(rho, prm.E0, prm.Emin, prm.p)
+            K = o.assemble_stiffness(g, dofs, E / prm.E0, k_unit)
+            t1 = time.perf_counter()
+            Kbc, fbc, _ = o.apply_dirichlet(K, f.copy(), pres)
+            t2 = time.perf_counter()
+            u = o.solve_direct(Kbc, fbc)
+            t3 = time.perf_counter()
+            energies.append(0.5 * float(u @ (Kbc @ u)))
+            t4 = time.perf_counter()
+            dc = o.sensitivities(g, dofs, rho, u, prm.E0, prm.Emin, prm.nu, prm.p, k0)
+            t5 = time.perf_counter()
+            dcf = o.filter_sensitivity(fc, rho, dc)
+            t6 = time.perf_counter()
+            rho, _, _, _ = o.optimality_criteria_update(rho, dcf, dv, prm.volume_fraction, Vtot, V, prm.move_limit, prm.damping, fc, False)
+            t7 = time.perf_counter()
+            for k, d in zip(ph, (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4, t6 - t5, t7 - t6)):
+                ph[k] += d
+
+    if threadpool_limits is not None:
+        with threadpool_limits(limits=threads):
+            loop()
+    else:
+        loop()
+    total = sum(ph.values())
+    return {"threads": threads, "iterations": n_iter, "seconds_per_iteration": total / n_iter,
+            "phase_seconds_per_iteration": {k: v / n_iter for k, v in ph.items()}, "energies": energies}
+
+
+def gpu_c1(n_iter):
+    """the CUDA path on the same 60x20x4 problem, same number of SIMP iterations (Jacobi-PCG to rtol 1e-10, device-resident)"""
+    import easysimp_b200 as es
+    from oracle import simp_oracle as o
+
+    g, dofs, f, pres = o.cantilever_problem((60, 20, 4))
+    ctx = es.Context(0)
+    ctx.set_params(volume_fraction=0.5, filter_radius=1.5 * o.estimate_element_size(g), pcg_rtol=1e-10, pcg_maxit=200000, warm_start=1)
+    ctx.set_grid_structured(60, 20, 4, 1.0, 1.0, 1.0, dofs)
+    ctx.set_dirichlet(pres)
+    ctx.set_load(f)
+    ctx.filter_build_structured()
+    ctx.init_design(None)
+    ctx.iterate()  # lazy allocations, constant uploads
+    ctx.init_design(None)
+    t0 = time.perf_counter()
+    st = [ctx.iterate() for _ in range(n_iter)]
+    dt = time.perf_counter() - t0
+    ctx.close()
+    return {"seconds_per_iteration": dt / n_iter, "energies": [s.energy for s in st], "pcg_iters": [s.pcg_iters for s in st], "solver": "Jacobi-PCG fp64, rtol 1e-10"}
+
+
+def cpu_baseline_measured(n_iter, with_gpu):
+    out = {"config": "README cantilever 60x20x4 (BASELINE config 1), 4 800 cells, 19 215 dofs; the reference's path: sparse assembly + apply! + "
+                     "sparse direct solve (SuperLU here, CHOLMOD in the reference) + sensitivities + filter + OC, run to completion",
+           "kind": "port (oracle/simp_oracle.py)", "single_thread": cpu_direct_path(n_iter, 1)}
+    nt = host_threads()
+    if nt > 1:
+        out["all_cores"] = cpu_direct_path(n_iter, nt)
+    if with_gpu:
+        out["cuda_path_same_problem"] = gpu_c1(n_iter)
+        e_cpu, e_gpu = np.array(out["single_thread"]["energies"]), np.array(out["cuda_path_same_problem"]["energies"])
+        out["compliance_max_rel_diff"] = float(np.max(np.abs(e_cpu - e_gpu) / e_cpu))
+    return out
 
 
 def run_reference(args):
+    """the reference arm: the CPU port on the box's host cores (rank 0 only), a bounded sample per step"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     nel = WORKLOADS[args.workload]
-    iters, calib = calibrated_pcg_iters(args.workload, args.pcg_rtol)
-    vals = []
-    base = None
-    for _ in range(args.warmup + args.steps):
-        base = cpu_sample(nel, args, iters, n_pcg=2)
-        vals.append(base["seconds_per_step"])
-    t_step = float(np.mean(vals[args.warmup:]))
+    iters, note, same_window = jacobi_pcg_iters(args.workload, args.warmup, args.steps)
+    # 1 warm-up + 2 measured samples (the sample does not depend on the SIMP iteration: repeating it K times measures nothing new)
+    n_warm, n_meas = min(args.warmup, 1), max(1, min(args.steps, 2))
+    vals, base = [], None
+    for i in range(n_warm + n_meas):
+        base = cpu_sample(nel, args, iters, note, n_pcg=2)
+        if i >= n_warm:
+            vals.append(base["seconds_per_step"])
+    t_step = float(np.mean(vals))
     base["value"] = 1.0 / t_step
     out = {"impl": "reference", "metric": "simp_iters_per_sec", "value": 1.0 / t_step, "unit": "iter/s", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "strong",
-           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": workload_config(args, nel, iters, "calibrated (bench_calibration.json)" if calib else "nominal"),
-           "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+           "steps": n_meas, "warmup": n_warm, "steps_requested": args.steps, "warmup_requested": args.warmup,
+           "ms_per_step": 1e3 * t_step, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "extrapolated": True, "same_config": False,
+           "same_config_note": "CPU port = Jacobi-PCG (neither the reference's CHOLMOD nor this repo's multigrid CG); its PCG iteration count per step is "
+                               "taken from a Jacobi-PCG run of the CUDA arm on the same SIMP iterations" + ("" if same_window else " (window not covered by the calibration)"),
+           "config": workload_config(args, nel, iters, note, solver="Jacobi-PCG fp64 (CPU port), warm start"),
+           "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample", "extrapolated")},
            "e2e": {"value": 1.0 / t_step, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(out), flush=True)
 
 
-def workload_config(args, nel, pcg_iters, pcg_note):
+def workload_config(args, nel, pcg_iters, pcg_note, solver=None):
     nx, ny, nz = nel
+    if solver is None:
+        solver = ("CG fp64 + geometric-multigrid V(2,2) Chebyshev-Jacobi preconditioner (fp64)" if args.precond == "gmg" else "Jacobi-PCG fp64") + ", warm start"
     return {"workload": f"hex cantilever {nx}x{ny}x{nz} unit cubes, {nx * ny * nz} cells, {3 * (nx + 1) * (ny + 1) * (nz + 1)} dofs",
             "volume_fraction": args.volfrac, "p": 3.0, "E0": 1.0, "Emin": 1e-9, "nu": 0.3, "filter": "sensitivity",
-            "filter_radius": args.filter_radius, "move_limit": 0.2, "damping": 0.5,
-            "solver": ("CG fp64 + geometric-multigrid V(2,2) Chebyshev-Jacobi preconditioner" if args.precond == "gmg" and args.impl == "b200"
-                       else "CG fp64 + geometric-multigrid V(2,2) Chebyshev-Jacobi preconditioner evaluated in fp32"
-                       if args.precond == "gmg32" and args.impl == "b200" else "Jacobi-PCG fp64") + ", warm start",
+            "filter_radius": args.filter_radius, "move_limit": 0.2, "damping": 0.5, "solver": solver,
             "pcg_rtol": args.pcg_rtol, "mean_pcg_iters_per_step": pcg_iters, "pcg_iters_source": pcg_note,
+            "simp_iterations_timed": f"{args.warmup + 1}..{args.warmup + args.steps} from the uniform start design",
             "partition": f"x-slabs over {args.gpus} GPU(s)", "l2": "inputs_larger_than_l2 (813 MB per vector vs 126 MB L2)"}
 
 
+# ------------------------------------------------------------------------------------------------ CUDA arm
 def run_b200(args):
     import torch
 
@@ -203,7 +330,7 @@ def run_b200(args):
     pres, f = cantilever(nel)
     ctx = es.Context(local)
     ctx.set_params(volume_fraction=args.volfrac, filter_radius=args.filter_radius, pcg_rtol=args.pcg_rtol, pcg_maxit=200000,
-                   pcg_check_every=50, matvec_variant=args.variant, warm_start=1, precond={"jacobi": 0, "gmg": 1, "gmg32": 2}[args.precond])
+                   pcg_check_every=50, matvec_variant=args.variant, warm_start=1, precond={"jacobi": 0, "gmg": 1}[args.precond])
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
@@ -214,7 +341,6 @@ def run_b200(args):
     ctx.set_dirichlet(pres)
     ctx.set_load(f)
     ctx.filter_build_structured()
-    ctx.init_design(None)
     del f
 
     def barrier():
@@ -223,10 +349,15 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    stats = []
-    for _ in range(args.warmup):
-        stats.append(ctx.iterate())
-    # ---- timed region: K device-resident iterations
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- timed region 1: K device-resident iterations after W warm-up iterations from the uniform design
+    ctx.init_design(None)
+    stats = [ctx.iterate() for _ in range(args.warmup)]
     sampler = ClockSampler(local)
     sampler.start()  # started before the barrier so that it is already polling when the timed region begins
     ctx.profile_enable(True)
@@ -241,33 +372,33 @@ def run_b200(args):
     launches = ctx.launch_count - launches0
     mv_ms, mv_n, mv_bytes = ctx.profile_matvec()
     op_ms_all, op_n_all = ctx.profile_operator_all()
+    kernels = ctx.profile_kernels()
     ctx.profile_enable(False)
     dev_ms = sum(s.ms_total for s in timed)  # CUDA events on the library's stream, per iterate
-    t_local = torch.tensor([max(wall, dev_ms * 1e-3)], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t_local, op=dist.ReduceOp.MAX)
-    t_timed = float(t_local.item())
-    # ---- e2e: the same step through the C ABI with host buffers (pinned), copies inside the timed region
+    t_timed = max_over_ranks(max(wall, dev_ms * 1e-3))
+    # ---- timed region 2 (e2e): the SAME iterations through the C ABI with host buffers (pinned), copies inside the timed region
     e2e = None
     if not args.no_e2e:
         n_cells = nx * ny * nz
         rho_host = torch.empty(n_cells, dtype=torch.float64).pin_memory().numpy()
-        rho_host[:] = ctx.get_design()
+        ctx.init_design(None)  # back to the uniform design, displacement guess zero: the same W + K iterations again
+        for _ in range(args.warmup):
+            ctx.iterate()
+        ctx.get_design(out=rho_host)
         barrier()
         t0 = time.perf_counter()
+        e2e_stats = []
         for _ in range(args.steps):
             ctx.set_design(rho_host)          # H2D: design densities, 8 B/cell
-            s = ctx.iterate()
+            e2e_stats.append(ctx.iterate())
             ctx.get_design(out=rho_host)      # D2H into the pinned buffer: updated design (Optimization.jl:360) + 7 scalars
-            timed.append(s)
         barrier()
-        t_e2e = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-        e2e = {"value": args.steps / float(t_e2e.item()), "unit": "iter/s", "h2d_bytes_per_step": 8 * n_cells,
-               "d2h_bytes_per_step": 8 * n_cells + 8 * 7}
+        t_e2e = max_over_ranks(time.perf_counter() - t0)
+        e2e = {"value": args.steps / t_e2e, "unit": "iter/s", "h2d_bytes_per_step": 8 * n_cells, "d2h_bytes_per_step": 8 * n_cells + 8 * 7,
+               "same_iterations_as_value": True,
+               "max_rel_energy_diff_vs_value_run": float(max(abs(a.energy - b.energy) / abs(b.energy) for a, b in zip(e2e_stats, timed)))}
     if rank == 0:
-        pcg_iters = float(np.mean([s.pcg_iters for s in timed[:args.steps]]))
+        pcg_iters = float(np.mean([s.pcg_iters for s in timed]))
         peak, peak_src = measured_peak()
         achieved = mv_bytes / (mv_ms / max(mv_n, 1)) / 1e6 if mv_n else None  # GB/s per rank
         traffic = None
@@ -275,28 +406,54 @@ def run_b200(args):
             traffic = json.load(open(ROOT / "profiles" / "traffic.json")).get(f"{args.workload}_n{world}")
         except Exception:
             pass
+        # algorithmic bytes per launch of the other fine-grid kernels on this rank (SURVEY 8d conventions)
+        n_cell_r = nx * ny * nz / world
+        n_dof_r = (mv_bytes - 8.0 * n_cell_r) / 16.0 if mv_bytes else 3.0 * (nx + 1) * (ny + 1) * (nz + 1) / world
+        per_launch = {"operator_smoother": 48 * n_dof_r + 8 * n_cell_r, "operator_residual": 24 * n_dof_r + 8 * n_cell_r,
+                      "filter_stencil": 24 * n_cell_r, "sens_energy": 8 * n_dof_r + 16 * n_cell_r, "oc_volumes": 16 * n_cell_r,
+                      "prolong_fine": (16 + 1 + 1 / 3) * n_dof_r, "restrict_fine": (8 + 1) * n_dof_r, "mg_update_first": 48 * n_dof_r,
+                      "mg_direction": 40 * n_dof_r}
+        others = {}
+        for k, nb in per_launch.items():
+            ms, cnt = kernels.get(k, (0.0, 0))
+            if cnt:
+                gbs = nb / (ms / cnt) / 1e6
+                others[k] = {"launches": cnt, "avg_launch_ms": ms / cnt, "algorithmic_bytes_per_launch": nb, "achieved": gbs, "unit": "GB/s",
+                             "frac": gbs / peak, "share_of_step": ms / (1e3 * t_timed)}
         out = {"metric": "simp_iters_per_sec", "value": args.steps / t_timed, "unit": "iter/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": 1e3 * t_timed / args.steps, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                "config": workload_config(args, nel, pcg_iters, "measured in the timed region"),
                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
-               "roofline": {"bound": "hbm", "kernel": "k_matvec_fused (hex8 operator apply)", "achieved": achieved, "peak": peak,
+               "roofline": {"bound": "hbm", "kernel": "hex8 operator apply, plain / plain + <p,Ap> store modes (k_matvec_sweep; k_matvec_fused on coarse levels)",
+                            "achieved": achieved, "peak": peak,
                             "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": traffic,
                             "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src}); sustained (kernel timed inside the step)",
                             "algorithmic_bytes_per_launch": mv_bytes, "launches_timed": int(mv_n), "avg_launch_ms": mv_ms / max(mv_n, 1),
                             "share_of_step": op_ms_all / (1e3 * t_timed) if op_n_all else None,
-                            "share_note": f"all {op_n_all} fine-grid launches of k_matvec_fused (plain/dot applies + the modes that fuse the multigrid "
+                            "share_note": f"all {op_n_all} fine-grid launches of the operator kernel (plain/dot applies + the modes that fuse the multigrid "
                                           f"smoother step / residual into the store); achieved/frac use the {mv_n} plain/dot launches only"},
-               "phases_ms_per_step": {k: float(np.mean([getattr(s, k) for s in timed[:args.steps]])) for k in ("ms_filter", "ms_solve", "ms_sens", "ms_oc")},
+               "roofline_others": others,
+               "phases_ms_per_step": {k: float(np.mean([getattr(s, k) for s in timed])) for k in ("ms_filter", "ms_solve", "ms_sens", "ms_oc")},
                "history": [{"energy": s.energy, "change": s.change, "pcg_iters": s.pcg_iters, "pcg_relres": s.pcg_relres, "oc_steps": s.oc_steps}
                            for s in stats + timed]}
         if world == 1 and not args.no_cpu_baseline:
-            # the CPU port is Jacobi-PCG: scale its sample with ITS iteration count (measured once with the same
-            # Jacobi-PCG on the GPU, bench_calibration.json), not with this arm's multigrid count
-            cb = cpu_sample(nel, args, pcg_iters if args.precond == "jacobi" else calibrated_pcg_iters(args.workload, args.pcg_rtol)[0])
-            out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(out), flush=True)
+            # the CPU port is Jacobi-PCG: scale its sample with ITS iteration count on the same SIMP iterations (measured once with
+            # the same Jacobi-PCG on the GPU, bench_calibration.json), not with this arm's multigrid count
+            if args.precond == "jacobi":
+                it_cpu, note = pcg_iters, "this run's own Jacobi-PCG count"
+            else:
+                it_cpu, note, _ = jacobi_pcg_iters(args.workload, args.warmup, args.steps)
+            cb = cpu_sample(nel, args, it_cpu, note)
+            out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample", "extrapolated")}
     ctx.close()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.cpu_measured_iters > 0:
+        try:
+            out["cpu_baseline_measured"] = cpu_baseline_measured(args.cpu_measured_iters, with_gpu=True)
+        except Exception as e:  # the measured small-problem leg must never cost the headline line
+            out["cpu_baseline_measured"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 

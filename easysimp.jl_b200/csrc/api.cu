@@ -186,6 +186,13 @@ int esimp_set_params(esimp_ctx* ctx, const esimp_params* p) {
     bool nu_changed = p->nu != ctx->prm.nu;
     if (p->precond != ESIMP_PRECOND_JACOBI && p->precond != ESIMP_PRECOND_GMG && p->precond != ESIMP_PRECOND_GMG_FP32)
         return esimp_fail(ctx, ESIMP_ERR_ARG, "unknown preconditioner");
+    // The FP32 V-cycle is experimental: on its first GPU run (round 2, profiles/r2_gmg_fp32_first_gpu_run.log) it solved every case to
+    // the FP64 answer but needed 285 instead of 184 CG iterations on an anisotropic grid, so it is not a supported option.
+    if (p->precond == ESIMP_PRECOND_GMG_FP32) {
+        const char* e = getenv("ESIMP_EXPERIMENTAL_GMG_FP32");
+        if (!e || atoi(e) != 1)
+            return esimp_fail(ctx, ESIMP_ERR_ARG, "ESIMP_PRECOND_GMG_FP32 is experimental (set ESIMP_EXPERIMENTAL_GMG_FP32=1 to try it)");
+    }
     bool r_changed = p->filter_radius != ctx->prm.filter_radius;
     ctx->prm = *p;
     if (nu_changed) {
@@ -745,8 +752,10 @@ int esimp_profile_enable(esimp_ctx* ctx, int on) {
         for (auto& e : ctx->prof_ev) ESIMP_CUDA(cudaEventCreate(&e));
     }
     ctx->prof_on = on != 0;
-    ctx->prof_ms = ctx->prof_ms_other = 0.0;
-    ctx->prof_count = ctx->prof_count_other = 0;
+    for (int c = 0; c < 16; ++c) {
+        ctx->prof_ms_cat[c] = 0.0;
+        ctx->prof_cnt_cat[c] = 0;
+    }
     return ESIMP_OK;
 }
 // 16 B per owned dof (read u, write y) + 8 B per owned cell (read E); the row pads of the device layout are not counted
@@ -759,8 +768,8 @@ int esimp_profile_matvec(esimp_ctx* ctx, double* ms_sum, int64_t* count, double*
     CHECK_CTX();
     ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));
     ESIMP_TRY(prof_collect(ctx));
-    if (ms_sum) *ms_sum = ctx->prof_ms;
-    if (count) *count = ctx->prof_count;
+    if (ms_sum) *ms_sum = ctx->prof_ms_cat[PROF_OP_PLAIN];
+    if (count) *count = ctx->prof_cnt_cat[PROF_OP_PLAIN];
     if (bytes_per_apply)
         *bytes_per_apply = algorithmic_bytes_per_apply(ctx);
     return ESIMP_OK;
@@ -770,8 +779,20 @@ int esimp_profile_operator_all(esimp_ctx* ctx, double* ms_sum_all, int64_t* coun
     CHECK_CTX();
     ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));
     ESIMP_TRY(prof_collect(ctx));
-    if (ms_sum_all) *ms_sum_all = ctx->prof_ms + ctx->prof_ms_other;
-    if (count_all) *count_all = ctx->prof_count + ctx->prof_count_other;
+    if (ms_sum_all) *ms_sum_all = ctx->prof_ms_cat[PROF_OP_PLAIN] + ctx->prof_ms_cat[PROF_OP_SMOOTH] + ctx->prof_ms_cat[PROF_OP_RESID];
+    if (count_all) *count_all = ctx->prof_cnt_cat[PROF_OP_PLAIN] + ctx->prof_cnt_cat[PROF_OP_SMOOTH] + ctx->prof_cnt_cat[PROF_OP_RESID];
+    return ESIMP_OK;
+}
+
+int esimp_profile_kernels(esimp_ctx* ctx, int n, double* ms_sum, int64_t* count) {
+    CHECK_CTX();
+    if (n < 0 || n > 16 || !ms_sum || !count) return esimp_fail(ctx, ESIMP_ERR_ARG, "bad arguments");
+    ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));
+    ESIMP_TRY(prof_collect(ctx));
+    for (int c = 0; c < n; ++c) {
+        ms_sum[c] = ctx->prof_ms_cat[c];
+        count[c] = ctx->prof_cnt_cat[c];
+    }
     return ESIMP_OK;
 }
 

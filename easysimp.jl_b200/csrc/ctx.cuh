@@ -161,10 +161,22 @@ struct esimp_ctx {
     std::vector<cudaEvent_t> prof_ev;
     std::vector<uint8_t> prof_tag;
     int prof_n = 0;
-    double prof_ms = 0.0, prof_ms_other = 0.0;
-    int64_t prof_count = 0, prof_count_other = 0;
+    double prof_ms_cat[16] = {0};    // summed kernel time per category (PROF_* below)
+    int64_t prof_cnt_cat[16] = {0};
 };
-int prof_collect(esimp_ctx* ctx);  // vector_ops.cu: fold finished event pairs into prof_ms / prof_count
+int prof_collect(esimp_ctx* ctx);  // vector_ops.cu: fold finished event pairs into prof_ms_cat / prof_cnt_cat
+// kernel categories of the in-region timing (fine grid only; multigrid levels reuse the kernels on coarser grids)
+enum { PROF_OP_PLAIN = 0, PROF_OP_SMOOTH = 1, PROF_OP_RESID = 2, PROF_FILTER = 3, PROF_SENS = 4, PROF_OC_VOLUMES = 5, PROF_PROLONG = 6,
+       PROF_RESTRICT = 7, PROF_MG_UPDATE_FIRST = 8, PROF_MG_DIRECTION = 9, PROF_NCAT = 10 };
+// bracket the launches between PROF_BEGIN and PROF_END with an event pair on the context's stream while profiling is on
+#define PROF_BEGIN(ctx, cat, cond)                                                                         \
+    const bool _prof_timed = (ctx)->prof_on && (cond) && 2 * (ctx)->prof_n + 1 < (int)(ctx)->prof_ev.size(); \
+    if (_prof_timed) {                                                                                     \
+        (ctx)->prof_tag[(ctx)->prof_n] = (cat);                                                            \
+        cudaEventRecord((ctx)->prof_ev[2 * (ctx)->prof_n], (ctx)->stream);                                 \
+    }
+#define PROF_END(ctx) \
+    if (_prof_timed) cudaEventRecord((ctx)->prof_ev[2 * (ctx)->prof_n++ + 1], (ctx)->stream);
 
 int esimp_fail(esimp_ctx* ctx, int code, const std::string& msg);
 

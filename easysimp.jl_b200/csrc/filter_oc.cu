@@ -197,8 +197,10 @@ static int filter_apply(esimp_ctx* ctx, const double* a, const double* b, double
     if (ctx->structured) {
         ESIMP_TRY(upload_stencil(ctx));
         auto kern = k_filter_stencil<MODE>;
+        PROF_BEGIN(ctx, PROF_FILTER, true)
         LAUNCH_STREAM(kern, ctx->g, ctx->own_e0, ctx->own_e1, ctx->st_n, ctx->hx * ctx->hy * ctx->hz, a, b,
                       ctx->d_filtD, out);
+        PROF_END(ctx)
     } else {
         const UnstructuredMesh& um = ctx->um;
         auto kern = k_filter_csr<MODE>;
@@ -298,8 +300,12 @@ static int oc_update_multisection(esimp_ctx* ctx, const double* rho, const doubl
                 nhi[2 * n + 2] = nhi[n];
             }
         }
-        LAUNCH_STREAM(k_oc_volumes, rho, t, vol, vuni, sc, move, (long long)ctx->own_cell0, (long long)ctx->own_cell1, ctx->d_partial,
-                      ctx->d_ticket, out);
+        {
+            PROF_BEGIN(ctx, PROF_OC_VOLUMES, true)
+            LAUNCH_STREAM(k_oc_volumes, rho, t, vol, vuni, sc, move, (long long)ctx->own_cell0, (long long)ctx->own_cell1, ctx->d_partial,
+                          ctx->d_ticket, out);
+            PROF_END(ctx)
+        }
         ESIMP_TRY(allreduce_scalars(ctx, SC_OC0, OC_M, false));
         ESIMP_TRY(fetch_scalars(ctx));
         int n = 0;

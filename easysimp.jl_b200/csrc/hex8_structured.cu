@@ -256,7 +256,7 @@ static int launch_fused_tt(esimp_ctx* ctx, const OpView& vw, const T* E_t, bool 
     // only fine-grid applies are timed (multigrid levels reuse this kernel on coarser grids)
     // every fine-grid launch is timed; tag 0 = plain / dot applies (the roofline number), 1 = fused smoother / residual modes
     const bool timed = ctx->prof_on && fine && 2 * ctx->prof_n + 1 < (int)ctx->prof_ev.size();
-    if (timed) ctx->prof_tag[ctx->prof_n] = MODE <= FUSE_DOT ? 0 : 1;
+    if (timed) ctx->prof_tag[ctx->prof_n] = MODE <= FUSE_DOT ? PROF_OP_PLAIN : (MODE == FUSE_RESID ? PROF_OP_RESID : PROF_OP_SMOOTH);
     if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
     kern<<<grid, block, smem, ctx->stream>>>(g, vw.mv_e0, vw.mv_e1, vw.own_p0, vw.own_p1, chunk, E_t, d_in, d_out,
                                              ctx->d_partial_mv, ctx->d_ticket + 2, dot_out, fa);
@@ -373,7 +373,7 @@ static int launch_sweep_r(esimp_ctx* ctx, const OpView& vw, bool fine, const dou
         ESIMP_TRY(make_map3(ctx, &tmOpx[b], ops[b], nz1, ny1, n3, g.nzp, g.plane, 2, SW_OROWS, 3));
     }
     const bool timed = ctx->prof_on && fine && 2 * ctx->prof_n + 1 < (int)ctx->prof_ev.size();
-    if (timed) ctx->prof_tag[ctx->prof_n] = MODE <= FUSE_DOT ? 0 : 1;
+    if (timed) ctx->prof_tag[ctx->prof_n] = MODE <= FUSE_DOT ? PROF_OP_PLAIN : (MODE == FUSE_RESID ? PROF_OP_RESID : PROF_OP_SMOOTH);
     if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
     kern<<<dim3(nty, nchunk), SW_THREADS, smem, ctx->stream>>>(a, tmU, tmE, tmOp[0], tmOp[1], tmOp[2], tmOpx[0], tmOpx[1], tmOpx[2]);
     if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n++ + 1], ctx->stream);
@@ -643,9 +643,11 @@ __global__ void __launch_bounds__(256) k_sens_energy(GridDev g, int le0, int le1
 int hex8_sens_energy(esimp_ctx* ctx) {
     ESIMP_TRY(hex8_upload_constants(ctx));
     RedOut<1> out{{ctx->d_scal + SC_ENERGY}};
+    PROF_BEGIN(ctx, PROF_SENS, true)
     k_sens_energy<<<RED_BLOCKS, 256, 0, ctx->stream>>>(ctx->g, ctx->own_e0, ctx->own_e1, ctx->d_u, ctx->d_phys,
                                                        ctx->d_E, ctx->prm.p, ctx->prm.E0 - ctx->prm.Emin, ctx->d_dc,
                                                        ctx->d_partial, ctx->d_ticket, out);
+    PROF_END(ctx)
     ctx->launches++;
     ESIMP_CUDA(cudaGetLastError());
     return allreduce_scalars(ctx, SC_ENERGY, 1, false);

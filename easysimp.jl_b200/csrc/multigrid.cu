@@ -537,14 +537,20 @@ static int mg_vcycle(esimp_ctx* ctx, int l, bool first_done = false, int dot_slo
         LocalScope ls(ctx, true);
         ESIMP_TRY(mg_vcycle(ctx, l + 1));
     } else {
-        LAUNCH_STREAM(k_restrict, L.vw.g, C.vw.g, C.vw.own_p0, C.vw.own_p1, L.d_q, C.d_mask, C.d_r);
+        {
+            PROF_BEGIN(ctx, PROF_RESTRICT, l == 0)
+            LAUNCH_STREAM(k_restrict, L.vw.g, C.vw.g, C.vw.own_p0, C.vw.own_p1, L.d_q, C.d_mask, C.d_r);
+            PROF_END(ctx)
+        }
         ESIMP_TRY(mg_vcycle(ctx, l + 1));
         if (ctx->nranks > 1) ESIMP_TRY(comm_halo_nodes_lv(ctx, C.vw.g, C.vw.own_p0, C.vw.own_p1, C.has_left, C.has_right, C.d_z));
     }
     {
         const int nyz = (C.vw.g.ny + 1) * (C.vw.g.nz + 1);  // one thread per coarse (J,K) position
         dim3 grid((unsigned)std::min(64, (nyz + 255) / 256), (unsigned)std::min(65535, (L.vw.own_p1 - L.vw.own_p0) * 3));
+        PROF_BEGIN(ctx, PROF_PROLONG, l == 0)
         k_prolong_add<<<grid, 256, 0, ctx->stream>>>(L.vw.g, C.vw.g, L.vw.own_p0, L.vw.own_p1, C.d_z, L.d_mask, L.d_z);
+        PROF_END(ctx)
         ctx->launches++;
         ESIMP_CUDA(cudaGetLastError());
     }
@@ -604,8 +610,12 @@ int pcg_solve_mg(esimp_ctx* ctx, int* iters, double* relres) {
             // r -= alpha q, <r,r>, and the first Chebyshev step of the coming V-cycle (d = z = Dinv r / theta)
             const double lmax0 = L0.lmax, theta0 = 0.5 * (lmax0 + lmax0 / ctx->mg_ratio);
             RedOut<1> out{{S + SC_RR0}};
-            LAUNCH_STREAM(k_mg_update_first, ctx->d_q, ctx->d_r, L0.d_dinv, 1.0 / theta0, L0.d_d, L0.d_z, i0, i1, S + RZ[cur], S + SC_PQ,
+{
+                PROF_BEGIN(ctx, PROF_MG_UPDATE_FIRST, true)
+                LAUNCH_STREAM(k_mg_update_first, ctx->d_q, ctx->d_r, L0.d_dinv, 1.0 / theta0, L0.d_d, L0.d_z, i0, i1, S + RZ[cur], S + SC_PQ,
                           ctx->d_partial, ctx->d_ticket, out);
+                PROF_END(ctx)
+            }
             ESIMP_TRY(allreduce_scalars(ctx, SC_RR0, 1, false));
         }
         ++it;
@@ -625,7 +635,11 @@ int pcg_solve_mg(esimp_ctx* ctx, int* iters, double* relres) {
             LAUNCH_STREAM(k_dot2, ctx->d_r, L0.d_z, i0, i1, ctx->d_partial, ctx->d_ticket, out);
         }
         ESIMP_TRY(allreduce_scalars(ctx, RZ[nxt], 1, false));
-        LAUNCH_STREAM(k_mg_direction, L0.d_z, ctx->d_p, ctx->d_u, i0, i1, S + RZ[nxt], S + RZ[cur], S + SC_PQ, 0);
+        {
+            PROF_BEGIN(ctx, PROF_MG_DIRECTION, true)
+            LAUNCH_STREAM(k_mg_direction, L0.d_z, ctx->d_p, ctx->d_u, i0, i1, S + RZ[nxt], S + RZ[cur], S + SC_PQ, 0);
+            PROF_END(ctx)
+        }
     }
     if (rr > tol2) status = ESIMP_WARN_PCG_MAXIT;
     if (iters) *iters = it;

@@ -113,13 +113,9 @@ int prof_collect(esimp_ctx* ctx) {
     for (int i = 0; i < ctx->prof_n; ++i) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]) == cudaSuccess) {
-            if (ctx->prof_tag[i] == 0) {
-                ctx->prof_ms += ms;
-                ctx->prof_count++;
-            } else {
-                ctx->prof_ms_other += ms;
-                ctx->prof_count_other++;
-            }
+            const int cat = ctx->prof_tag[i] < 16 ? ctx->prof_tag[i] : 15;
+            ctx->prof_ms_cat[cat] += ms;
+            ctx->prof_cnt_cat[cat]++;
         }
     }
     ctx->prof_n = 0;

@@ -84,6 +84,7 @@ _SIGNATURES = {
     "esimp_n_cells": (C.c_int64, [_P]),
     "esimp_bench_matvec": (C.c_int, [_P, C.c_int, _D, _D]),
     "esimp_bench_operator_mode": (C.c_int, [_P, C.c_int, C.c_int, _D, _D]),
+    "esimp_profile_kernels": (C.c_int, [_P, C.c_int, _D, C.POINTER(C.c_int64)]),
     "esimp_launch_count": (C.c_int64, [_P]),
     "esimp_set_design": (C.c_int, [_P, _D]),
     "esimp_profile_enable": (C.c_int, [_P, C.c_int]),
@@ -371,6 +372,17 @@ class Context:
         n = C.c_int64(0)
         self._chk(self.lib.esimp_profile_operator_all(self._h, C.byref(ms), C.byref(n)), "esimp_profile_operator_all")
         return ms.value, n.value
+
+    PROF_NAMES = ["operator_plain_dot", "operator_smoother", "operator_residual", "filter_stencil", "sens_energy", "oc_volumes",
+                  "prolong_fine", "restrict_fine", "mg_update_first", "mg_direction"]
+
+    def profile_kernels(self):
+        """{category: (summed kernel ms, launches)} of the in-region CUDA-event timing (esimp_profile_kernels)"""
+        n = len(self.PROF_NAMES)
+        ms = (C.c_double * n)()
+        cnt = (C.c_int64 * n)()
+        self._chk(self.lib.esimp_profile_kernels(self._h, n, ms, cnt), "esimp_profile_kernels")
+        return {k: (ms[i], int(cnt[i])) for i, k in enumerate(self.PROF_NAMES)}
 
     def bench_operator_mode(self, mode, reps):
         ms = C.c_double(0)

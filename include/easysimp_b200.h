@@ -223,6 +223,12 @@ int esimp_profile_matvec(esimp_ctx* ctx, double* ms_sum, int64_t* count, double*
 /* same clock over EVERY fine-grid launch of the operator kernel, including the modes that fuse the multigrid smoother
  * step / residual into the store phase (those move more bytes, so they are kept out of the roofline figure) */
 int esimp_profile_operator_all(esimp_ctx* ctx, double* ms_sum_all, int64_t* count_all);
+/* the same clock per kernel category, fine grid only (sum of kernel milliseconds and number of launches since
+ * esimp_profile_enable): 0 operator plain / plain + dot, 1 operator with the smoother step fused in, 2 operator residual
+ * mode, 3 filter stencil, 4 sensitivities + energy, 5 OC candidate volumes, 6 prolongation onto the fine grid,
+ * 7 restriction of the fine residual, 8 first smoother step fused with the CG update, 9 CG direction update.
+ * n <= 16 entries are written. */
+int esimp_profile_kernels(esimp_ctx* ctx, int n, double* ms_sum, int64_t* count);
 /* number of kernels this context has launched so far */
 int64_t esimp_launch_count(const esimp_ctx* ctx);
 

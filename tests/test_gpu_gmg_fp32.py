@@ -1,7 +1,8 @@
 """-m gpu tests of the opt-in FP32 V-cycle preconditioner (csrc/multigrid32.cu, precond = ESIMP_PRECOND_GMG_FP32).
 
-The code path was written after the round-1 GPU budget was spent and has NOT been run on a device yet, so these tests
-are skipped unless ESIMP_TEST_GMG_FP32=1 is set:
+First GPU run (round 2, profiles/r2_gmg_fp32_first_gpu_run.log): every case converged to the FP64 answer, but the
+anisotropic 24x12x6 grid needed 285 CG iterations against 184 with the FP64 V-cycle (bar: 1.5x + 2), so the path stays
+experimental -- the library refuses it unless ESIMP_EXPERIMENTAL_GMG_FP32=1 -- and these tests run only on request:
     ESIMP_TEST_GMG_FP32=1 python -m pytest tests/test_gpu_gmg_fp32.py -m gpu -q
 They hold the path to the same bars as the FP64 V-cycle: solve vs sparse direct 1e-6, loop compliance 1e-6 relative,
 densities 1e-3, and an iteration count within 1.5x of the FP64 preconditioner.
@@ -15,7 +16,10 @@ from oracle import simp_oracle as o
 from test_gpu_parity import _run_loop, make_ctx, relmax
 
 pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("ESIMP_TEST_GMG_FP32") != "1", reason="opt-in path, not yet validated on a GPU")]
+              pytest.mark.skipif(os.environ.get("ESIMP_TEST_GMG_FP32") != "1",
+                                 reason="experimental path: first GPU run (round 2) missed the iteration-count bar on an anisotropic grid")]
+if os.environ.get("ESIMP_TEST_GMG_FP32") == "1":
+    os.environ["ESIMP_EXPERIMENTAL_GMG_FP32"] = "1"  # the library refuses the experimental preconditioner without it
 
 
 @pytest.mark.parametrize("nel,right", [((32, 16, 16), (32.0, 16.0, 16.0)), ((40, 20, 20), (2.0, 1.0, 1.0)), ((24, 12, 6), (24.0, 6.0, 1.5))])

@@ -201,6 +201,14 @@ def _golden_case(gpu_ctx_factory, golden_dir, name, problem, pcg_rtol):
     assert np.max(np.abs(energy - gz["energy"]) / gz["energy"]) < 1e-6
     assert np.max(np.abs(np.array([s.volume for s in stats]) - gz["volume"]) / gz["volume"]) < 1e-9
     assert np.max(np.abs(np.array([s.change for s in stats]) - gz["change"])) < 1e-4
+    # the other logged scalars of the loop (Optimization.jl:374-379, OptimizationLogger.jl:50-60): grayness = fraction of cells
+    # with 0.1 < rho~ < 0.9 (a cell within 1e-3 of a threshold may fall either side: a handful of cells), max |u| like the
+    # compliance, and the Lagrange multiplier the bisection ends on (same midpoints; the |dV| < 1e-6 break may come a step apart)
+    n_cells = g.n_cells
+    assert np.max(np.abs(np.array([s.grayness for s in stats]) - gz["grayness"])) <= 5.0 / n_cells + 1e-12
+    assert np.max(np.abs(np.array([s.max_u for s in stats]) - gz["max_u"]) / gz["max_u"]) < 1e-6
+    assert np.max(np.abs(np.array([s.lam for s in stats]) - gz["lam"]) / gz["lam"]) < 1e-4
+    assert np.max(np.abs(np.array([s.oc_steps for s in stats]) - gz["oc_steps"])) <= 2
     e_fin, v_fin, _ = ctx.final_analysis()
     assert abs(e_fin - gz["final_energy"][0]) / gz["final_energy"][0] < 1e-6
     # final density field L_inf <= 1e-3 after the fixed iteration count (north_star)
@@ -317,7 +325,7 @@ def test_operator_properties_c4(gpu_ctx_factory, nel):
     y = 2 * o.splitmix64(idx, 2) - 1
     rho = 1e-3 + (1 - 1e-3) * o.splitmix64(np.arange(n_cells, dtype=np.uint64), 3)
     results = {}
-    for name in ("fused16x16", "fused_atomic8x32", "fused8x32", "fused8x16"):
+    for name in ("fused16x16", "fused_atomic8x32", "fused8x32", "fused8x16", "sweep"):
         ctx = gpu_ctx_factory()
         ctx.set_params(matvec_variant=VARIANTS[name])
         ctx.set_grid_structured(nx, ny, nz, 1.0, 1.0, 1.0, None)
@@ -334,6 +342,60 @@ def test_operator_properties_c4(gpu_ctx_factory, nel):
     assert relmax(results["fused_atomic8x32"], results["fused16x16"]) < 1e-12
     assert relmax(results["fused8x32"], results["fused16x16"]) < 1e-12
     assert relmax(results["fused8x16"], results["fused16x16"]) < 1e-12
+    assert relmax(results["sweep"], results["fused16x16"]) < 1e-12
+
+
+def test_first_simp_iteration_c4_against_cpu_port(gpu_ctx_factory):
+    """One SIMP iteration at BASELINE config 4 (240x80x80, 1.536 M cells, 4.74 M dofs), stage by stage, against the C / OpenMP
+    restatement oracle/cpu_simp.c (itself held against the numpy oracle in tests/test_cpu_port.py): the CUDA solve
+    (multigrid CG, rtol 1e-10) satisfies the CPU port's system to 1e-9, compliance 1e-6, element sensitivities and the
+    sensitivity filter 1e-10, the OC update ends on the same multiplier and the same design."""
+    from bench import cantilever
+    from oracle import cpu_port as cp
+
+    nel = (240, 80, 80)
+    nx, ny, nz = nel
+    pres, f = cantilever(nel)
+    n_cells = nx * ny * nz
+    rho = np.full(n_cells, 0.5)
+    ctx = gpu_ctx_factory()
+    ctx.set_params(volume_fraction=0.5, filter_radius=1.5, pcg_rtol=1e-10, pcg_maxit=20000, pcg_check_every=5, precond=1)
+    ctx.set_grid_structured(nx, ny, nz, 1.0, 1.0, 1.0, None)
+    ctx.set_dirichlet(pres)
+    ctx.set_load(f)
+    ctx.filter_build_structured()
+    ctx.set_density(rho)
+    u, iters, relres, st = ctx.solve()
+    assert st == 0 and relres <= 1e-10
+    dc, energy = ctx.sensitivities()
+    dcf = ctx.filter_sens(rho, dc)
+    dv = np.full(n_cells, 1.0 / n_cells)
+    rho_new, lam, steps, _ = ctx.oc(rho, dcf, dv)
+    ctx.close()
+    # ---- the CPU port on the same inputs
+    g1 = o.generate_grid_hex((1, 1, 1))
+    K0 = np.ascontiguousarray(o.hex8_ke(g1.coords[g1.cells[0]], *o.lame(1.0, 0.3)))
+    E = cp.modulus(rho, 1.0, 1e-9, 3.0)
+    fixed = np.zeros(f.size, dtype=np.uint8)
+    fixed[pres] = 1
+    Ku = cp.matvec(nel, K0, E, fixed, 1.0, u)
+    free = fixed == 0
+    assert np.linalg.norm((f - Ku)[free]) / np.linalg.norm(f[free]) < 1e-9      # u solves the CPU port's system
+    assert abs(0.5 * float(u @ Ku) - energy) / energy < 1e-6                    # compliance (Optimization.jl:320)
+    dc_cpu, en_cpu = cp.sensitivities(nel, K0, rho, E, u, 1.0, 1e-9, 3.0)
+    assert relmax(dc, dc_cpu) < 1e-10 and abs(en_cpu - energy) / energy < 1e-9
+    assert relmax(dcf, cp.filter_sens(nel, (1.0, 1.0, 1.0), 1.5, rho, dc_cpu)) < 1e-10
+    lo, hi, new_cpu, lam_cpu = 1e-9, 1e9, None, 0.0
+    for _ in range(200):  # OptimalityCriteria.jl:98-137 on the CPU port's candidate / volume kernel
+        lam_cpu = 0.5 * (lo + hi)
+        new_cpu, v = cp.oc_step(rho, dcf, dv, lam_cpu, 0.2, 0.5, 1.0)
+        err = v - 0.5 * n_cells
+        if abs(err) < 1e-6:
+            break
+        lo, hi = (lam_cpu, hi) if err > 0 else (lo, lam_cpu)
+    # at this size the volume sums carry ~1e-4 of absolute rounding noise, far above the |dV| < 1e-6 break: both bisections run until
+    # the bracket collapses, possibly a few steps apart
+    assert abs(lam - lam_cpu) / lam_cpu < 1e-4 and np.abs(rho_new - new_cpu).max() < 1e-4
 
 
 def test_solution_properties_c4(gpu_ctx_factory):
