@@ -354,6 +354,51 @@ static int download_cells(esimp_ctx* ctx, const double* d_local, double* h) {
     return ESIMP_OK;
 }
 
+// Multi-rank structured grids: only the x-slab of a cell array moves.  The caller's numbering is x fastest (cell = i + nx (j + ny k)),
+// so a slab of w layers is ny*nz runs of w doubles with pitch nx: one cudaMemcpy2DAsync each way instead of the whole array.
+__global__ void k_gather_cells_slab(GridDev g, int l0, int w, const double* __restrict__ src, double* __restrict__ dst) {
+    const long long n = (long long)w * g.eplane;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % g.nz);
+        const long long t = i / g.nz;
+        const int j = (int)(t % g.ny), l = (int)(t / g.ny);
+        dst[g.cell(l0 + l, j, k)] = src[l + (long long)w * (j + (long long)g.ny * k)];
+    }
+}
+__global__ void k_scatter_cells_slab(GridDev g, int l0, int w, const double* __restrict__ src, double* __restrict__ dst) {
+    const long long n = (long long)w * g.eplane;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % g.nz);
+        const long long t = i / g.nz;
+        const int j = (int)(t % g.ny), l = (int)(t / g.ny);
+        dst[l + (long long)w * (j + (long long)g.ny * k)] = src[g.cell(l0 + l, j, k)];
+    }
+}
+// host array -> the stored layers [l0, l0 + w) of a local cell array
+static int upload_cells_slab(esimp_ctx* ctx, const double* h, double* d_local, int l0, int w) {
+    const GridDev& g = ctx->g;
+    ESIMP_TRY(ensure_stage(ctx, (int64_t)w * g.eplane));
+    ESIMP_CUDA(cudaMemcpy2DAsync(ctx->d_stage, sizeof(double) * w, h + g.ge0 + l0, sizeof(double) * g.nx, sizeof(double) * w, (size_t)g.eplane,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    k_gather_cells_slab<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(g, l0, w, ctx->d_stage, d_local);
+    ctx->launches++;
+    ESIMP_CUDA(cudaGetLastError());
+    return ESIMP_OK;
+}
+// the OWNED layers of a local cell array -> the matching entries of the host array (nothing else is written)
+static int download_cells_slab(esimp_ctx* ctx, const double* d_local, double* h) {
+    const GridDev& g = ctx->g;
+    const int l0 = ctx->own_e0, w = ctx->own_e1 - ctx->own_e0;
+    ESIMP_TRY(ensure_stage(ctx, (int64_t)w * g.eplane));
+    k_scatter_cells_slab<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(g, l0, w, d_local, ctx->d_stage);
+    ctx->launches++;
+    ESIMP_CUDA(cudaGetLastError());
+    ESIMP_CUDA(cudaMemcpy2DAsync(h + g.ge0 + l0, sizeof(double) * g.nx, ctx->d_stage, sizeof(double) * w, sizeof(double) * w, (size_t)g.eplane,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));
+    return ESIMP_OK;
+}
+
 int esimp_set_load(esimp_ctx* ctx, const double* f) {
     CHECK_CTX();
     NEED(ctx->structured || ctx->unstructured, "no mesh");
@@ -710,6 +755,8 @@ int esimp_stress_tensors(esimp_ctx* ctx, int64_t cell0, int64_t n, double* sigma
 int esimp_get_design(esimp_ctx* ctx, double* rho) {
     CHECK_CTX();
     if (!rho) return esimp_fail(ctx, ESIMP_ERR_ARG, "NULL array");
+    // multi-rank: only the cells this rank owns are written (the entries of other ranks' slabs stay untouched)
+    if (ctx->nranks > 1 && ctx->structured) return download_cells_slab(ctx, ctx->d_rho, rho);
     return download_cells(ctx, ctx->d_rho, rho);
 }
 int esimp_get_physical_density(esimp_ctx* ctx, double* rho) {
@@ -734,10 +781,14 @@ int esimp_set_design(esimp_ctx* ctx, const double* rho) {
     CHECK_CTX();
     NEED(ctx->design_set, "esimp_init_design first");
     if (!rho) return esimp_fail(ctx, ESIMP_ERR_ARG, "NULL array");
-    ESIMP_TRY(upload_cells(ctx, rho, ctx->d_rho));
     // multi-rank: the caller's array is authoritative only on the cells this rank owns (esimp_get_design fills
-    // nothing else), so the ghost layers are refreshed from their owners
-    if (ctx->nranks > 1 && ctx->structured) ESIMP_TRY(comm_halo_cells(ctx, ctx->d_rho));
+    // nothing else): only that slab is uploaded, the ghost layers are refreshed from their owners
+    if (ctx->nranks > 1 && ctx->structured) {
+        ESIMP_TRY(upload_cells_slab(ctx, rho, ctx->d_rho, ctx->own_e0, ctx->own_e1 - ctx->own_e0));
+        ESIMP_TRY(comm_halo_cells(ctx, ctx->d_rho));
+    } else {
+        ESIMP_TRY(upload_cells(ctx, rho, ctx->d_rho));
+    }
     ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));
     return ESIMP_OK;
 }

@@ -482,7 +482,8 @@ static int mg_smooth(esimp_ctx* ctx, MGLevel& L, int k, bool zero_guess, bool fi
         if (!first_done) LAUNCH_STREAM(k_cheb_first, L.d_r, L.d_dinv, 1.0 / theta, L.d_d, L.d_z, L.own_dof0, L.own_dof1);
         done = 1;
     }
-    const bool fused = ctx->prm.matvec_variant == ESIMP_MATVEC_AUTO || ctx->prm.matvec_variant == ESIMP_MATVEC_FUSED;
+    const bool fused = ctx->prm.matvec_variant == ESIMP_MATVEC_AUTO || ctx->prm.matvec_variant == ESIMP_MATVEC_FUSED ||
+                       ctx->prm.matvec_variant == ESIMP_MATVEC_SWEEP;  // SWEEP by name: every store mode of the sweep kernel (tests)
     for (int i = done; i < k; ++i) {
         if (!fused) ESIMP_TRY(mg_apply(ctx, L, L.d_z, L.d_q));
         double c1, c2;
@@ -516,7 +517,8 @@ static int mg_vcycle(esimp_ctx* ctx, int l, bool first_done = false, int dot_slo
         return mg_smooth(ctx, L, l == 0 ? ctx->mg_nu : ctx->mg_coarse_its, true, first_done, dot_slot, dot_done);
     MGLevel& C = ctx->mg[l + 1];
     ESIMP_TRY(mg_smooth(ctx, L, ctx->mg_nu, true, first_done));
-    if (ctx->prm.matvec_variant == ESIMP_MATVEC_AUTO || ctx->prm.matvec_variant == ESIMP_MATVEC_FUSED) {
+    if (ctx->prm.matvec_variant == ESIMP_MATVEC_AUTO || ctx->prm.matvec_variant == ESIMP_MATVEC_FUSED ||
+        ctx->prm.matvec_variant == ESIMP_MATVEC_SWEEP) {
         // residual fused into the operator's store: q = r - A z (prescribed rows are zeroed by the fix-up: z = 0 there)
         if (ctx->nranks > 1) ESIMP_TRY(comm_halo_nodes_lv(ctx, L.vw.g, L.vw.own_p0, L.vw.own_p1, L.has_left, L.has_right, L.d_z));
         ESIMP_TRY(hex8_resid_view(ctx, L.vw, L.d_z, L.d_q, L.d_r));

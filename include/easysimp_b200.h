@@ -198,7 +198,11 @@ int esimp_stress_tensors(esimp_ctx* ctx, int64_t cell0, int64_t n, double* sigma
 int esimp_stress_nq(const esimp_ctx* ctx);
 
 /* ---- state I/O ------------------------------------------------------------------------- */
-int esimp_get_design(esimp_ctx* ctx, double* rho);           /* design variables           */
+/* design variables.  On a multi-rank structured context only the x-slab this rank owns moves: esimp_get_design writes the
+ * entries of its own cells and leaves the rest of `rho` untouched, esimp_set_design reads only those entries (ghost layers come
+ * from their owners) -- 8 B per owned cell each way instead of the whole array on every rank.  The other getters keep
+ * writing zeros outside the owned slab, so that per-rank results can be summed. */
+int esimp_get_design(esimp_ctx* ctx, double* rho);
 int esimp_get_physical_density(esimp_ctx* ctx, double* rho); /* filtered (== design for :sensitivity) */
 int esimp_get_displacement(esimp_ctx* ctx, double* u);       /* caller's dof numbering     */
 int esimp_set_displacement(esimp_ctx* ctx, const double* u);
