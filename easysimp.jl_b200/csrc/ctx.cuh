@@ -209,8 +209,10 @@ bool hex8_matvec_fuses_dot(const esimp_ctx* ctx);
 OpView fine_view(const esimp_ctx* ctx);
 int hex8_matvec_view(esimp_ctx* ctx, const OpView& vw, const double* d_in, double* d_out, int variant, int dot_slot);
 int hex8_diagonal_view(esimp_ctx* ctx, const OpView& vw, double* dinv, long long n_dofs_global, double* diag_value);
+// dmode (FUSE_D_* of fused_kernel.cuh): 1 = the previous direction is read from d, 2 = it is z_in itself (first step after a zero guess),
+// 3 = it is z_in - zprev (zprev may alias z_out); write_d = 0 drops the store of the new direction
 int hex8_smooth_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double* z_out, const double* r, const double* dinv,
-                     double* d, double c1, double c2, int dot_slot = -1);
+                     double* d, double c1, double c2, int dot_slot = -1, int dmode = 1, int write_d = 1, const double* zprev = nullptr);
 int hex8_resid_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double* res_out, const double* r);
 bool hex8_sweep_eligible(const esimp_ctx* ctx, const OpView& vw);
 int hex8_smooth_view_f32(esimp_ctx* ctx, const OpView& vw, const float* E, const float* z_in, float* z_out, const float* r,

@@ -138,6 +138,10 @@ __device__ __forceinline__ void cp_async_scalar(float* smem_dst, const float* gs
 //   FUSE_PLAIN  y = s                                  FUSE_DOT     y = s and <u, y> (PCG)
 //   FUSE_SMOOTH one Chebyshev-Jacobi step of the multigrid smoother with u = z:
 //               v = c1 d + c2 Dinv (r - s);  d = v;  y = z + v      (Dinv is 0 on prescribed dofs)
+//               The previous direction d need not be a stored vector (FuseArgsT::dmode): after the first step from a zero
+//               guess d IS the iterate z (FUSE_D_IS_Z), later it is z - z_prev (FUSE_D_FROM_ZPREV: z_prev is the input
+//               buffer of the previous step, which this step overwrites in place -- every thread reads its own node of
+//               z_prev before it stores there); write_d = 0 then drops the store of d as well: 32-40 B/dof instead of 48
 //   FUSE_RESID  y = r - s                              (residual that is restricted to the next level)
 // r, Dinv, d of the plane are prefetched into registers at the start of the step (before the FP64 work), so
 // their latency is covered; the operator is FP64-bound, the extra bytes ride for free.
@@ -148,6 +152,9 @@ struct FuseArgsT {
     const T* dinv = nullptr;
     T* d = nullptr;
     T c1 = T(0), c2 = T(0);
+    int dmode = FUSE_D_BUFFER;   // where the previous Chebyshev direction comes from (ignored when c1 == 0)
+    int write_d = 1;             // store the new direction into d
+    const T* zprev = nullptr;    // FUSE_D_FROM_ZPREV: the iterate before z (may alias the output vector)
 };
 using FuseArgs = FuseArgsT<double>;
 // T = double: the operator of the FP64 solve.  T = float: the same kernel for the single-precision multigrid cycle
@@ -161,6 +168,8 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
     constexpr bool SMOOTH = MODE == FUSE_SMOOTH || MODE == FUSE_SMOOTH_DOT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NF = SMOOTH ? 3 : (MODE == FUSE_RESID ? 1 : 0);
+    // previous Chebyshev direction: a stored vector, z - z_prev, or (neither flag, c1 != 0) the iterate itself; c1 == 0: unused
+    const bool d_buffer = SMOOTH && fa.c1 != T(0) && fa.dmode == FUSE_D_BUFFER, d_zprev = SMOOTH && fa.c1 != T(0) && fa.dmode == FUSE_D_FROM_ZPREV;
     FusedSmem<T, TY, TZ, NF>& sm = *reinterpret_cast<FusedSmem<T, TY, TZ, NF>*>(smem_raw);
     const int tid = threadIdx.x;
     const int tz = tid % TZ, ty = tid / TZ;
@@ -235,9 +244,11 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
                 if (own_store) {
                     if (SMOOTH) {
                         const T rv = sm.fz[0][c][ty][tz];
-                        const T v = fma(fa.c1, sm.fz[2 % NF][c][ty][tz], fa.c2 * sm.fz[1 % NF][c][ty][tz] * (rv - s));
-                        (fa.d + foff)[c * plane] = v;
-                        const T znew = sm.in[ring][c][ty][tz] + v;  // the input plane is still in its ring slot
+                        const T zin = sm.in[ring][c][ty][tz];  // the input plane is still in its ring slot
+                        const T dprev = d_buffer ? sm.fz[2 % NF][c][ty][tz] : (d_zprev ? zin - sm.fz[2 % NF][c][ty][tz] : zin);
+                        const T v = fma(fa.c1, dprev, fa.c2 * sm.fz[1 % NF][c][ty][tz] * (rv - s));
+                        if (fa.write_d) (fa.d + foff)[c * plane] = v;
+                        const T znew = zin + v;
                         py[c * plane] = znew;
                         if (MODE == FUSE_SMOOTH_DOT) pq[0] = fma((double)rv, (double)znew, pq[0]);  // <r, z>: the PCG scalar of the next iteration
                     } else if (MODE == FUSE_RESID) {
@@ -270,7 +281,7 @@ __global__ void __launch_bounds__(TY* TZ, MINB) k_matvec_fused(GridDev g, int le
                 cp_async_scalar(&sm.fz[0][c][ty][tz], fa.r + foff + c * plane, true);
                 if (SMOOTH) {
                     cp_async_scalar(&sm.fz[1 % NF][c][ty][tz], fa.dinv + foff + c * plane, true);
-                    cp_async_scalar(&sm.fz[2 % NF][c][ty][tz], fa.d + foff + c * plane, fa.c1 != T(0));
+                    if (d_buffer || d_zprev) cp_async_scalar(&sm.fz[2 % NF][c][ty][tz], (d_zprev ? fa.zprev : fa.d) + foff + c * plane, true);
                 }
             }
         }

@@ -37,6 +37,9 @@ struct GridDev {
 // node-row pitch for nz cells per row
 ESIMP_HD int esimp_node_pitch(int nz) { return (nz + 1 + 7) & ~7; }
 
+// where the fused Chebyshev step of the operator kernels takes the previous direction d from (FuseArgsT::dmode)
+enum { FUSE_D_NONE = 0, FUSE_D_BUFFER = 1, FUSE_D_IS_Z = 2, FUSE_D_FROM_ZPREV = 3 };
+
 // where a grid reduction leaves its NV results (device pointers)
 template <int NV>
 struct RedOut {

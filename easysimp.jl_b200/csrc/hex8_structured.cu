@@ -349,7 +349,8 @@ static int launch_sweep_r(esimp_ctx* ctx, const OpView& vw, bool fine, const dou
     a.d_out = fa.d;
     a.c1 = fa.c1;
     a.c2 = fa.c2;
-    a.have_d = fa.c1 != 0.0 ? 1 : 0;
+    a.dmode = fa.c1 != 0.0 ? fa.dmode : FUSE_D_NONE;
+    a.write_d = fa.write_d;
     static const int pfd = getenv("ESIMP_SWEEP_PFD") ? atoi(getenv("ESIMP_SWEEP_PFD")) : 0;
     a.pf_dist = pfd;
     const long long nblk = (long long)nty * nchunk;
@@ -367,7 +368,7 @@ static int launch_sweep_r(esimp_ctx* ctx, const OpView& vw, bool fine, const dou
     ESIMP_TRY(make_map3(ctx, &tmU, d_in, nz1, ny1, n3, g.nzp, g.plane, SW_BOXZ, SW_ROWS, 3));
     ESIMP_TRY(make_map3(ctx, &tmE, vw.E, g.nz, g.ny, g.NEX, g.nz, g.eplane, 32, SW_CROWS, 1));
     for (int b = 0; b < 3; ++b) tmOp[b] = tmOpx[b] = tmU;
-    const double* ops[3] = {fa.r, fa.dinv, fa.d};
+    const double* ops[3] = {fa.r, fa.dinv, fa.dmode == FUSE_D_FROM_ZPREV ? fa.zprev : fa.d};
     for (int b = 0; b < TR::NF; ++b) {  // r | r, Dinv, d: exactly the owned nodes of a segment, and the extra column nz
         ESIMP_TRY(make_map3(ctx, &tmOp[b], ops[b], nz1, ny1, n3, g.nzp, g.plane, 32, SW_OROWS, 3));
         ESIMP_TRY(make_map3(ctx, &tmOpx[b], ops[b], nz1, ny1, n3, g.nzp, g.plane, 2, SW_OROWS, 3));
@@ -437,7 +438,7 @@ int hex8_matvec_view(esimp_ctx* ctx, const OpView& vw, const double* d_in, doubl
 }
 // multigrid smoother step / residual fused into the operator's store (16x16 owner tiles: measured faster than 8x16 for these modes)
 int hex8_smooth_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double* z_out, const double* r, const double* dinv,
-                     double* d, double c1, double c2, int dot_slot) {
+                     double* d, double c1, double c2, int dot_slot, int dmode, int write_d, const double* zprev) {
     ESIMP_TRY(hex8_upload_constants(ctx));
     FuseArgs fa;
     fa.r = r;
@@ -445,6 +446,9 @@ int hex8_smooth_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, doubl
     fa.d = d;
     fa.c1 = c1;
     fa.c2 = c2;
+    fa.dmode = dmode;
+    fa.write_d = write_d;
+    fa.zprev = zprev;
     // smoother modes: 48 B/dof make them memory-latency bound, where the round-1 kernel's 16 warps per SM win (r2, 512x256x256:
     // 1.29 ms vs 1.39 ms for the sweep kernel's 8 warps).  ESIMP_SWEEP_SMOOTH=1 (or naming the variant) selects the sweep kernel.
     static const int sweep_smooth = getenv("ESIMP_SWEEP_SMOOTH") ? atoi(getenv("ESIMP_SWEEP_SMOOTH")) : 0;

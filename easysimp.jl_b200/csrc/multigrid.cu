@@ -132,11 +132,12 @@ __global__ void __launch_bounds__(256) k_prolong_add(GridDev gf, GridDev gc, int
 }
 
 // Chebyshev-Jacobi: first step from a zero guess: d = Dinv r / theta, z = d
+// (d = nullptr: the fused smoother takes the first direction from z itself, FUSE_D_IS_Z, and d is never stored)
 __global__ void k_cheb_first(const double* __restrict__ r, const double* __restrict__ dinv, double inv_theta, double* __restrict__ d,
                              double* __restrict__ z, long long i0, long long i1) {
     for (long long i = i0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (long long)gridDim.x * blockDim.x) {
         double v = dinv[i] * r[i] * inv_theta;
-        d[i] = v;
+        if (d) d[i] = v;
         z[i] = v;
     }
 }
@@ -221,7 +222,7 @@ __global__ void k_mg_update_first(const double* __restrict__ q, double* __restri
         r[i] = ri;
         acc[0] = fma(ri, ri, acc[0]);
         double v = dinv[i] * ri * inv_theta;
-        d[i] = v;
+        if (d) d[i] = v;  // nullptr with the fused smoother (FUSE_D_IS_Z): 40 B/dof instead of 48
         z[i] = v;
     }
     grid_reduce<1, false>(acc, partial, ticket, out);
@@ -469,6 +470,11 @@ int mg_setup(esimp_ctx* ctx) {
     return ESIMP_OK;
 }
 
+// the operator kernels fuse the Chebyshev update / the residual into their store phase
+static bool mg_fused(const esimp_ctx* ctx) {
+    const int v = ctx->prm.matvec_variant;
+    return v == ESIMP_MATVEC_AUTO || v == ESIMP_MATVEC_FUSED || v == ESIMP_MATVEC_SWEEP;  // SWEEP by name: every store mode of the sweep kernel (tests)
+}
 // k Chebyshev-Jacobi iterations on level L for A z = r
 // first_done: the zero-guess first step was already applied by the caller (k_mg_update_first)
 // dot_slot >= 0: the last fused step also leaves <r, z> in d_scal[dot_slot]; *dot_done reports whether it did
@@ -478,12 +484,11 @@ static int mg_smooth(esimp_ctx* ctx, MGLevel& L, int k, bool zero_guess, bool fi
     const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
     double rho = 1.0 / sigma;
     int done = 0;
+    const bool fused = mg_fused(ctx);
     if (zero_guess) {
-        if (!first_done) LAUNCH_STREAM(k_cheb_first, L.d_r, L.d_dinv, 1.0 / theta, L.d_d, L.d_z, L.own_dof0, L.own_dof1);
+        if (!first_done) LAUNCH_STREAM(k_cheb_first, L.d_r, L.d_dinv, 1.0 / theta, fused ? nullptr : L.d_d, L.d_z, L.own_dof0, L.own_dof1);
         done = 1;
     }
-    const bool fused = ctx->prm.matvec_variant == ESIMP_MATVEC_AUTO || ctx->prm.matvec_variant == ESIMP_MATVEC_FUSED ||
-                       ctx->prm.matvec_variant == ESIMP_MATVEC_SWEEP;  // SWEEP by name: every store mode of the sweep kernel (tests)
     for (int i = done; i < k; ++i) {
         if (!fused) ESIMP_TRY(mg_apply(ctx, L, L.d_z, L.d_q));
         double c1, c2;
@@ -500,7 +505,10 @@ static int mg_smooth(esimp_ctx* ctx, MGLevel& L, int k, bool zero_guess, bool fi
             // Chebyshev update fused into the operator's store: z' = z + c1 d + c2 Dinv (r - A z)
             if (ctx->nranks > 1) ESIMP_TRY(comm_halo_nodes_lv(ctx, L.vw.g, L.vw.own_p0, L.vw.own_p1, L.has_left, L.has_right, L.d_z));
             const bool with_dot = dot_slot >= 0 && i == k - 1;
-            ESIMP_TRY(hex8_smooth_view(ctx, L.vw, L.d_z, L.d_z2, L.d_r, L.d_dinv, L.d_d, c1, c2, with_dot ? dot_slot : -1));
+            // the previous direction is never a stored vector: z itself right after the zero-guess first step, z - z_prev later
+            // (z_prev = the input of the previous step = d_z2, which this step overwrites in place)
+            const int dmode = i == 0 ? FUSE_D_NONE : (i == 1 && zero_guess ? FUSE_D_IS_Z : FUSE_D_FROM_ZPREV);
+            ESIMP_TRY(hex8_smooth_view(ctx, L.vw, L.d_z, L.d_z2, L.d_r, L.d_dinv, L.d_d, c1, c2, with_dot ? dot_slot : -1, dmode, 0, L.d_z2));
             if (with_dot && dot_done) *dot_done = true;
             std::swap(L.d_z, L.d_z2);
         } else {
@@ -614,7 +622,7 @@ int pcg_solve_mg(esimp_ctx* ctx, int* iters, double* relres) {
             RedOut<1> out{{S + SC_RR0}};
 {
                 PROF_BEGIN(ctx, PROF_MG_UPDATE_FIRST, true)
-                LAUNCH_STREAM(k_mg_update_first, ctx->d_q, ctx->d_r, L0.d_dinv, 1.0 / theta0, L0.d_d, L0.d_z, i0, i1, S + RZ[cur], S + SC_PQ,
+                LAUNCH_STREAM(k_mg_update_first, ctx->d_q, ctx->d_r, L0.d_dinv, 1.0 / theta0, mg_fused(ctx) ? nullptr : L0.d_d, L0.d_z, i0, i1, S + RZ[cur], S + SC_PQ,
                           ctx->d_partial, ctx->d_ticket, out);
                 PROF_END(ctx)
             }

@@ -48,6 +48,9 @@ float c_Bf[8][3][3];
 
 // ---- cp.async model: immediate (copies land at issue) or deferred (they land when wait_group retires their group)
 static bool g_deferred_copies = false;
+// fused smoother step: source of the previous direction (FUSE_D_* of grid_dev.h: 1 = the d vector), store of the new one, z_prev
+static int g_dmode = 1, g_write_d = 1;
+static const double* g_zprev = nullptr;
 struct EmuCopy {
     void* dst;
     const void* src;
@@ -439,6 +442,9 @@ int emu_fused(int is_float, int mode, int nx, int ny, int nz, int chunk, const d
         fa.d = d;
         fa.c1 = c1;
         fa.c2 = c2;
+        fa.dmode = g_dmode;
+        fa.write_d = g_write_d;
+        fa.zprev = g_zprev;
         return run_mode<double>(mode, g, chunk, E, u, y, dot ? dot : &dummy, fa);
     }
     std::vector<float> Ef(E, E + nc), uf(u, u + nd), yf(nd), rf, df, dinvf;
@@ -466,6 +472,13 @@ int emu_fused(int is_float, int mode, int nx, int ny, int nz, int chunk, const d
 }
 
 void emu_set_deferred_tma(int on) { g_tma_deferred = on != 0; }
+// how the fused smoother step of both kernels gets its previous direction (FUSE_D_*), whether it stores the new one, and the
+// previous iterate for FUSE_D_FROM_ZPREV (device layout of the call that follows; may alias its output vector)
+void emu_set_smoother_direction(int dmode, int write_d, const double* zprev) {
+    g_dmode = dmode;
+    g_write_d = write_d;
+    g_zprev = zprev;
+}
 
 // One launch of the sweep kernel (sweep_kernel.cuh) on ONE x-slab (or the whole grid: gp0 = ge0 = 0, npx = nx + 1, nex = nx,
 // [ps0, ps1) = [0, nx + 1), [le0, le1) = [0, nx)).  Vectors in the library's device layout with node-row pitch nzp.
@@ -495,7 +508,8 @@ int emu_sweep(int mode, int nx, int ny, int nz, int nzp, int gp0, int npx, int g
     a.d_out = d;
     a.c1 = c1;
     a.c2 = c2;
-    a.have_d = c1 != 0.0;
+    a.dmode = c1 != 0.0 ? g_dmode : FUSE_D_NONE;
+    a.write_d = g_write_d;
     double dummy = 0.0;
     if (dot) *dot = 0.0;
     a.dot_out = RedOut<1>{{dot ? dot : &dummy}};
@@ -517,8 +531,8 @@ int emu_sweep(int mode, int nx, int ny, int nz, int nzp, int gp0, int npx, int g
         return t;
     };
     SwTensorMap tmU = node_map(u, SW_BOXZ, SW_ROWS), tmR = node_map(r, 32, SW_OROWS), tmDinv = node_map(dinv, 32, SW_OROWS),
-                tmD = node_map(d, 32, SW_OROWS), tmRx = node_map(r, 2, SW_OROWS), tmDinvx = node_map(dinv, 2, SW_OROWS),
-                tmDx = node_map(d, 2, SW_OROWS), tmE;
+                tmD = node_map(g_dmode == FUSE_D_FROM_ZPREV ? g_zprev : d, 32, SW_OROWS), tmRx = node_map(r, 2, SW_OROWS), tmDinvx = node_map(dinv, 2, SW_OROWS),
+                tmDx = node_map(g_dmode == FUSE_D_FROM_ZPREV ? g_zprev : d, 2, SW_OROWS), tmE;
     tmE.base = E;
     tmE.dim[0] = nz;
     tmE.dim[1] = ny;

@@ -130,7 +130,8 @@ struct SweepArgs {
     double* y;        // result vector (owned nodes of the owned planes)
     double* d_out;    // FUSE_SMOOTH: the Chebyshev direction is updated in place (read through the d tensor map)
     double c1, c2;
-    int have_d;       // FUSE_SMOOTH: c1 != 0 (the first step of a sweep has no previous direction)
+    int dmode;        // FUSE_SMOOTH: where the previous Chebyshev direction comes from (FUSE_D_*; FUSE_D_NONE when c1 == 0)
+    int write_d;      // FUSE_SMOOTH: store the new direction into d_out
     int pf_dist;      // producer: planes by which the L2 prefetch runs ahead of the shared-memory loads (0 = none)
     double* partial;
     unsigned int* ticket;
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
                     if (NF > 0 && lp >= P0 && lp < P1) {
                         const int fs = t % SM::FN;
                         if (t >= SM::FN) sw_bar_wait(&sm.fempty[fs], ((t / SM::FN) - 1) & 1);
-                        const int nb = NF == 1 ? 1 : (a.have_d ? 3 : 2);
+                        const int nb = NF == 1 ? 1 : ((a.dmode == FUSE_D_BUFFER || a.dmode == FUSE_D_FROM_ZPREV) ? 3 : 2);  // third box: d or z_prev
                         const bool xcol = extra && s == nseg - 1;  // the last segment also brings the operands of node column nz
                         sw_bar_expect_tx(&sm.ffull[fs], (unsigned)(nb * (SW_OP_BOX + (xcol ? SW_OPX_BOX : 0)) * 8));
                         const SwTensorMap* maps[6] = {&tmR, &tmDinv, &tmD, &tmRx, &tmDinvx, &tmDx};
@@ -352,10 +353,12 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
                         if (TR::SMOOTH) {
                             const double rv = op[0];
                             const double dinv = op[(1 % NFS) * ostride];
-                            const double dprev = a.have_d ? op[(2 % NFS) * ostride] : 0.0;
+                            const double zin = uin[c * SW_ROWS * SW_BOXZ + r * SW_BOXZ + col];
+                            const double dprev = a.dmode == FUSE_D_BUFFER ? op[(2 % NFS) * ostride]
+                                               : a.dmode == FUSE_D_FROM_ZPREV ? zin - op[(2 % NFS) * ostride] : zin;  // FUSE_D_IS_Z / unused
                             const double v = fma(a.c1, dprev, a.c2 * dinv * (rv - s_val));
-                            dp[off] = v;
-                            const double znew = uin[c * SW_ROWS * SW_BOXZ + r * SW_BOXZ + col] + v;
+                            if (a.write_d) dp[off] = v;
+                            const double znew = zin + v;
                             yp[off] = znew;
                             if (MODE == FUSE_SMOOTH_DOT) pq[0] = fma(rv, znew, pq[0]);
                         } else if (MODE == FUSE_RESID) {

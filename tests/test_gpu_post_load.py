@@ -214,7 +214,9 @@ def test_host_api_acceleration_and_stresses():
     sref = o.stresses_simp(g, dofs, res.displacements, 1.0, 0.3, 1e-9, 3.0, res.densities)
     st = res.stresses
     assert len(st) == g.n_cells and relmax(st.von_mises_q1, sref["vm_q1"]) < 1e-10 and relmax(st.von_mises_avg, sref["vm_avg"]) < 1e-10
-    assert st.max_cell == sref["max_cell"] and relmax(st[st.max_cell], sref["sigma"][st.max_cell]) < 1e-10
+    # the problem is mirror symmetric in z: cells (i, j, k) and (i, j, nz-1-k) carry the same stress up to rounding of the
+    # iterative solve, so the argmax may be either of the pair -- it must be A maximiser of the oracle's field
+    assert sref["vm_avg"][st.max_cell] >= sref["max_vm"] * (1 - 1e-10) and relmax(st[st.max_cell], sref["sigma"][st.max_cell]) < 1e-10
     assert 0.5 in res.checkpoints and len(res.checkpoints[0.5]["stresses"]) == g.n_cells
     data = es.create_results_data(grid, dh, cellvalues, res)
     assert relmax(data["element_energy"], sref["element_energy"]) < 1e-10 and data["displacement"].shape == (3, g.n_nodes)

@@ -23,6 +23,7 @@ def emu(request):
     assert path.exists(), "run __graft_entry__.build() first"
     lib = C.CDLL(str(path))
     lib.emu_sweep.argtypes = [C.c_int] * 14 + [D] * 6 + [C.c_double, C.c_double, D, D]
+    lib.emu_set_smoother_direction.argtypes = [C.c_int, C.c_int, D]
     lib.emu_set_deferred_tma(int(request.param == "tma_lands_later"))
     return lib
 
@@ -123,3 +124,28 @@ def test_x_slab_partition_reproduces_the_global_operator(emu, nranks, halo_e, ch
         assert np.isnan(y_loc[ghost]).all()
         covered[sl.gp0 + sl.own_p0:sl.gp0 + sl.own_p1] += 1
     assert (covered == 1).all()
+
+
+@pytest.mark.parametrize("nel,right,chunk", GRIDS[1:3])
+def test_direction_free_smoother_steps(emu, nel, right, chunk):
+    """the Chebyshev direction need not be a stored vector: right after the zero-guess first step it is the iterate itself
+    (FUSE_D_IS_Z = 2), later it is z - z_prev (FUSE_D_FROM_ZPREV = 3); the d vector is neither read (NaN in) nor written"""
+    p = Problem(nel, right, seed=5)
+    r = p.rng.standard_normal(p.nd)
+    dinv = 1.0 / (0.5 + p.rng.random(p.nd))
+    c1, c2 = 0.37, 0.81
+    z1 = 0.3 * dinv * r                               # first step from a zero guess: d1 = z1
+    z2_want = z1 + c1 * z1 + c2 * dinv * (r - p.A(z1))
+    emu.emu_set_smoother_direction(2, 0, None)
+    try:
+        y, dnew, _ = run(emu, p, SMOOTH, z1, chunk=chunk, r=r, dinv=dinv, d=np.full(p.nd, np.nan), c1=c1, c2=c2)
+        assert relmax(y, z2_want) < 1e-12 and np.isnan(dnew).all()
+        # next step: d2 = z2 - z1, z_prev handed in the device layout of the kernel under test
+        z3_want = z2_want + c1 * (z2_want - z1) + c2 * dinv * (r - p.A(z2_want))
+        zprev = pad_rows(p.to_dev(z1), p.nel)
+        emu.emu_set_smoother_direction(3, 0, ptr(zprev))
+        z1, keep = z2_want, zprev  # noqa: F841  (keep the buffer alive during the call)
+        y, dnew, dot = run(emu, p, SMOOTH_DOT, z1, chunk=chunk, r=r, dinv=dinv, d=np.full(p.nd, np.nan), c1=c1, c2=c2)
+        assert relmax(y, z3_want) < 1e-12 and np.isnan(dnew).all() and abs(dot - r @ z3_want) < 1e-10 * np.abs(r * z3_want).sum()
+    finally:
+        emu.emu_set_smoother_direction(1, 1, None)
