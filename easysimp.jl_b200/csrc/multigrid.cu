@@ -57,39 +57,48 @@ __global__ void k_restrict_E(GridDev gf, GridDev gc, int ce0, int ce1, const dou
 }
 
 // r_c = P' res_f on the owned coarse nodes (27-point full weighting), 0 on prescribed coarse dofs
-__global__ void k_restrict(GridDev gf, GridDev gc, int cp0, int cp1, const double* __restrict__ resf,
-                           const uint8_t* __restrict__ maskc, double* __restrict__ rc) {
-    long long n = (long long)(cp1 - cp0) * 3 * gc.plane;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
-        int K = (int)(idx % gc.nzp);
-        if (K > gc.nz) continue;  // pad entries of the node rows stay zero
-        long long t = idx / gc.nzp;
-        int J = (int)(t % (gc.ny + 1));
-        t /= (gc.ny + 1);
-        int c = (int)(t % 3);
-        int Lp = cp0 + (int)(t / 3);
-        double acc = 0.0;
-        if (!((maskc[gc.node(Lp, J, K)] >> c) & 1)) {
-            const int Gf = 2 * (gc.gp0 + Lp);
-            const int lpf = Gf - gf.gp0;
+__global__ void __launch_bounds__(256) k_restrict(GridDev gf, GridDev gc, int cp0, int cp1, const double* __restrict__ resf,
+                                                  const uint8_t* __restrict__ maskc, double* __restrict__ rc) {
+    // One thread per coarse dof: blockIdx.y walks the (coarse plane, component) pairs, the x dimension the (J, K) positions of a
+    // plane incl. the row pads (32-bit index arithmetic only), lanes along K.  Along z the three fine values 2K-1, 2K, 2K+1 come
+    // from ONE aligned 16-byte load (2K, 2K+1) plus the second half of the left neighbour lane's pair (the pad entries behind a
+    // fine row are zero, so 2K+1 past the last node contributes nothing): 9 coalesced 16-byte loads per node instead of 27
+    // stride-2 scalar ones.
+    const int nJK = (gc.ny + 1) * gc.nzp;
+    const int nJK_round = (nJK + 31) / 32 * 32;  // whole warps: the shuffles need every lane
+    const int lane = threadIdx.x & 31;
+    for (int pc = blockIdx.y; pc < (cp1 - cp0) * 3; pc += gridDim.y) {
+        const int Lp = cp0 + pc / 3, c = pc % 3;
+        const int Gf = 2 * (gc.gp0 + Lp), lpf = Gf - gf.gp0;
+        const uint8_t* __restrict__ mrow = maskc + (long long)Lp * gc.plane;
+        double* __restrict__ out = rc + (long long)(Lp * 3 + c) * gc.plane;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nJK_round; i += gridDim.x * blockDim.x) {
+            const bool in_range = i < nJK;
+            const int id = in_range ? i : nJK - 1;
+            const int J = id / gc.nzp, K = id - J * gc.nzp;
+            const bool node = in_range && K <= gc.nz;     // pad entries of the coarse rows stay zero
+            const bool left_in_lane = lane > 0 && K > 0;  // lane - 1 holds (J, K - 1) of the same row
+            const int kf = 2 * (K <= gc.nz ? K : gc.nz);  // pad threads read a valid address, their result is dropped
+            double acc = 0.0;
 #pragma unroll
             for (int dx = -1; dx <= 1; ++dx) {
-                if (Gf + dx < 0 || Gf + dx > gf.nx || lpf + dx < 0 || lpf + dx >= gf.NPX) continue;
+                const bool xok = !(Gf + dx < 0 || Gf + dx > gf.nx || lpf + dx < 0 || lpf + dx >= gf.NPX);
+                const double* __restrict__ fplane = resf + (long long)((xok ? lpf + dx : lpf) * 3 + c) * gf.plane;
 #pragma unroll
                 for (int dy = -1; dy <= 1; ++dy) {
-                    int jf = 2 * J + dy;
-                    if (jf < 0 || jf > gf.ny) continue;
-#pragma unroll
-                    for (int dz = -1; dz <= 1; ++dz) {
-                        int kf = 2 * K + dz;
-                        if (kf < 0 || kf > gf.nz) continue;
-                        double w = (dx ? 0.5 : 1.0) * (dy ? 0.5 : 1.0) * (dz ? 0.5 : 1.0);
-                        acc = fma(w, resf[gf.dof(lpf + dx, c, jf, kf)], acc);
-                    }
+                    const int jf = 2 * J + dy;
+                    const bool ok = xok && jf >= 0 && jf <= gf.ny;
+                    const double* row = fplane + (ok ? jf : 2 * J) * gf.nzp;
+                    double2 v = make_double2(0.0, 0.0);
+                    if (ok) v = *reinterpret_cast<const double2*>(row + kf);
+                    double left = __shfl_up_sync(0xffffffffu, v.y, 1);
+                    if (!left_in_lane) left = (ok && K > 0) ? row[kf - 1] : 0.0;
+                    const double w = (dx ? 0.5 : 1.0) * (dy ? 0.5 : 1.0);
+                    acc = fma(w, v.x + 0.5 * (v.y + left), acc);
                 }
             }
+            if (node) out[id] = ((mrow[id] >> c) & 1) ? 0.0 : acc;
         }
-        rc[gc.dof(Lp, c, J, K)] = acc;
     }
 }
 
@@ -119,13 +128,23 @@ __global__ void __launch_bounds__(256) k_prolong_add(GridDev gf, GridDev gc, int
                 v10 = 0.5 * (v10 + c1[o10]);
                 v11 = 0.5 * (v11 + c1[o11]);
             }
+            // the fine pair (2K, 2K+1) of a row is one aligned 16-byte read-modify-write (the row pitch is a multiple of 8 doubles;
+            // behind the last node, 2K+1 is a pad entry: it gets += 0 and stays zero)
             const int f00 = (2 * J) * nzf + 2 * K;
-            if (!((mrow[f00] >> c) & 1)) zrow[f00] += v00;
-            if (hasK && !((mrow[f00 + 1] >> c) & 1)) zrow[f00 + 1] += 0.5 * (v00 + v01);
+            {
+                double2* p = reinterpret_cast<double2*>(zrow + f00);
+                double2 z2 = *p;
+                if (!((mrow[f00] >> c) & 1)) z2.x += v00;
+                if (hasK && !((mrow[f00 + 1] >> c) & 1)) z2.y += 0.5 * (v00 + v01);
+                *p = z2;
+            }
             if (hasJ) {
                 const int f10 = f00 + nzf;
-                if (!((mrow[f10] >> c) & 1)) zrow[f10] += 0.5 * (v00 + v10);
-                if (hasK && !((mrow[f10 + 1] >> c) & 1)) zrow[f10 + 1] += 0.25 * ((v00 + v01) + (v10 + v11));
+                double2* p = reinterpret_cast<double2*>(zrow + f10);
+                double2 z2 = *p;
+                if (!((mrow[f10] >> c) & 1)) z2.x += 0.5 * (v00 + v10);
+                if (hasK && !((mrow[f10 + 1] >> c) & 1)) z2.y += 0.25 * ((v00 + v01) + (v10 + v11));
+                *p = z2;
             }
         }
     }
@@ -542,14 +561,25 @@ static int mg_vcycle(esimp_ctx* ctx, int l, bool first_done = false, int dot_slo
         // rest of the cycle without any communication; the prolongation back reads the local full coarse grid
         const int fp0g = L.vw.g.gp0 + L.vw.own_p0, fp1g = L.vw.g.gp0 + L.vw.own_p1;  // owned fine planes, global
         ESIMP_CUDA(cudaMemsetAsync(C.d_r, 0, sizeof(double) * C.ndof_loc, ctx->stream));
-        LAUNCH_STREAM(k_restrict, L.vw.g, C.vw.g, (fp0g + 1) / 2, (fp1g - 1) / 2 + 1, L.d_q, C.d_mask, C.d_r);
+        {
+            const int cp0 = (fp0g + 1) / 2, cp1 = (fp1g - 1) / 2 + 1;
+            const int nJK = (C.vw.g.ny + 1) * C.vw.g.nzp;
+            dim3 grid((unsigned)std::min(64, (nJK + 255) / 256), (unsigned)std::max(1, std::min(65535, (cp1 - cp0) * 3)));
+            k_restrict<<<grid, 256, 0, ctx->stream>>>(L.vw.g, C.vw.g, cp0, cp1, L.d_q, C.d_mask, C.d_r);
+            ctx->launches++;
+            ESIMP_CUDA(cudaGetLastError());
+        }
         ESIMP_TRY(comm_allreduce(ctx, C.d_r, C.ndof_loc, false));
         LocalScope ls(ctx, true);
         ESIMP_TRY(mg_vcycle(ctx, l + 1));
     } else {
         {
             PROF_BEGIN(ctx, PROF_RESTRICT, l == 0)
-            LAUNCH_STREAM(k_restrict, L.vw.g, C.vw.g, C.vw.own_p0, C.vw.own_p1, L.d_q, C.d_mask, C.d_r);
+            const int nJK = (C.vw.g.ny + 1) * C.vw.g.nzp;
+            dim3 grid((unsigned)std::min(64, (nJK + 255) / 256), (unsigned)std::max(1, std::min(65535, (C.vw.own_p1 - C.vw.own_p0) * 3)));
+            k_restrict<<<grid, 256, 0, ctx->stream>>>(L.vw.g, C.vw.g, C.vw.own_p0, C.vw.own_p1, L.d_q, C.d_mask, C.d_r);
+            ctx->launches++;
+            ESIMP_CUDA(cudaGetLastError());
             PROF_END(ctx)
         }
         ESIMP_TRY(mg_vcycle(ctx, l + 1));
