@@ -35,7 +35,7 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path[:0] = [str(ROOT), str(ROOT / "easysimp.jl_b200")]
 
-WORKLOADS = {"c5": (512, 256, 256), "c4": (240, 80, 80), "c1": (60, 20, 4)}
+WORKLOADS = {"c5": (512, 256, 256), "c4": (240, 80, 80), "c1": (60, 20, 4), "c3": None}  # c3: imported mesh (stul15 fixture), replicas only
 CALIB = ROOT / "bench_calibration.json"
 
 
@@ -308,6 +308,87 @@ def workload_config(args, nel, pcg_iters, pcg_note, solver=None):
             "partition": f"x-slabs over {args.gpus} GPU(s)", "l2": "inputs_larger_than_l2 (813 MB per vector vs 126 MB L2)"}
 
 
+# ------------------------------------------------------------------------------------------------ imported-mesh workload
+def run_b200_c3(args):
+    """BASELINE config 3 as a bench line: the reference's data/stul15.vtu (131 920 general hexahedra, 147 922 nodes; fixture
+    tests/golden/mesh_stul15_hex.npz) with the boundary conditions of test/Examples/04_gripper_complex.jl minus the body force,
+    element-by-element gather-scatter operator with graph colouring, CSR filter, Jacobi-PCG.  Replicas only (no slab partition)."""
+    import easysimp_b200 as es
+
+    z = np.load(ROOT / "tests" / "golden" / "mesh_stul15_hex.npz")
+    grid = es.Grid(z["points"].astype(np.float64), z["cells"].astype(np.int64), None)
+    ctx = es.Context(0)
+    ctx.set_params(E0=2.4e3, Emin=1e-6, nu=0.35, p=3.0, volume_fraction=0.3, pcg_rtol=args.pcg_rtol, pcg_maxit=200000, pcg_check_every=50,
+                   warm_start=1, precond=0)  # material before the mesh: the element data are built with nu
+    dh, cellvalues, K, f = es.setup_problem(grid, ctx=ctx)
+    fixed = es.select_nodes_by_circle(grid, [0.0, 75.0, 115.0], [0.0, -1.0, 0.0], 16.11, 1e-3)
+    sym = es.select_nodes_by_plane(grid, [0.0, 0.0, 0.0], [1.0, 0.0, 0.0], 1e-3)
+    leg = es.select_nodes_by_plane(grid, [0.0, 0.0, -90.0], [0.0, 0.0, 1.0], 1.0)
+    cam = es.select_nodes_by_circle(grid, [0.0, 0.0, 5.0], [0.0, 0.0, 1.0], 21.5, 1e-3)
+    don = dh.dof_of_node
+    pres = np.unique(np.concatenate([don[np.array(sorted(fixed))].ravel(), don[np.array(sorted(sym)), 0]])).astype(np.int64)
+    es.apply_force_(f, dh, sorted(leg), [0.0, 0.0, -13000.0])
+    es.apply_force_(f, dh, sorted(cam), [0.0, 0.0, -500.0])
+    vols = es.calculate_element_volumes(grid)
+    fc = es.create_filter_cache(grid, 1.5, vols)
+    ctx.set_params(filter_radius=fc.filter_radius)
+    ctx.set_dirichlet(pres)
+    ctx.set_load(f)
+    ctx.filter_build_csr(fc.rowptr, fc.col, fc.cell_centers, fc.element_volumes, fc.filter_radius)
+    ctx.init_design(None)
+    stats = [ctx.iterate() for _ in range(args.warmup)]
+    sampler = ClockSampler(0)
+    sampler.start()
+    ctx.profile_enable(True)
+    launches0 = ctx.launch_count
+    import torch
+
+    torch.cuda.synchronize()
+    sampler.rows.clear()
+    t0 = time.perf_counter()
+    timed = [ctx.iterate() for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    ms, cnt = ctx.profile_kernels()["um_matvec"]
+    ctx.profile_enable(False)
+    n_cells, n_dofs = grid.getncells(), dh.ndofs
+    # e2e: the same iterations again with the design travelling through host buffers
+    rho_host = torch.empty(n_cells, dtype=torch.float64).pin_memory().numpy()
+    ctx.init_design(None)
+    for _ in range(args.warmup):
+        ctx.iterate()
+    ctx.get_design(out=rho_host)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.set_design(rho_host)
+        ctx.iterate()
+        ctx.get_design(out=rho_host)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    peak, peak_src = measured_peak()
+    alg = 16.0 * n_dofs + (8.0 + 24 * 4 + 24 * 8) * n_cells  # u in, y out, E, the 24 dof ids and the 24 node coordinates of every cell
+    out = {"metric": "simp_iters_per_sec", "value": args.steps / wall, "unit": "iter/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "replicas only", "vs_baseline": None, "dtype": "f64",
+           "data": "reference mesh data/stul15.vtu (fixture), example-04 boundary conditions",
+           "config": {"workload": f"imported hex8 mesh stul15: {n_cells} cells, {n_dofs} dofs, gather-scatter operator with graph colouring",
+                      "E0": 2.4e3, "Emin": 1e-6, "nu": 0.35, "p": 3.0, "volume_fraction": 0.3, "filter": "sensitivity (CSR)", "filter_radius": 1.5,
+                      "solver": "Jacobi-PCG fp64, warm start", "pcg_rtol": args.pcg_rtol,
+                      "mean_pcg_iters_per_step": float(np.mean([s.pcg_iters for s in timed])), "l2": "working set (13 MB) fits L2: L2-assisted"},
+           "clocks": clocks, "gpu_launches": int(launches),
+           "e2e": {"value": args.steps / t_e2e, "unit": "iter/s", "h2d_bytes_per_step": 8 * n_cells, "d2h_bytes_per_step": 8 * n_cells + 56},
+           "roofline": {"bound": "hbm", "kernel": "k_um_matvec_hex_geom (one apply = memset + one launch per colour)", "achieved": alg / (ms / cnt) / 1e6 if cnt else None,
+                        "peak": peak, "unit": "GB/s", "frac": alg / (ms / cnt) / 1e6 / peak if cnt else None, "traffic": None,
+                        "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peak_src})", "algorithmic_bytes_per_launch": alg, "launches_timed": cnt,
+                        "avg_launch_ms": ms / cnt if cnt else None, "share_of_step": ms / (1e3 * wall) if cnt else None,
+                        "note": "latency / launch bound at this size (15-20 colour launches of a few thousand cells each); FP64 bound per cell"},
+           "history": [{"energy": s.energy, "change": s.change, "pcg_iters": s.pcg_iters} for s in stats + timed]}
+    print(json.dumps(out), flush=True)
+    ctx.close()
+
+
 # ------------------------------------------------------------------------------------------------ CUDA arm
 def run_b200(args):
     import torch
@@ -463,5 +544,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.workload == "c3":
+        run_b200_c3(a)
     else:
         run_b200(a)

@@ -56,6 +56,7 @@ static void free_mesh_state(esimp_ctx* ctx) {
     ctx->d_fload = nullptr;
     ctx->body_on = false;
     post_forget_ctx(ctx);
+    um_forget_ctx(ctx);
     ctx->stage_cap = 0;
     ctx->n_fixed = 0;
     um_free(ctx);

@@ -167,7 +167,7 @@ struct esimp_ctx {
 int prof_collect(esimp_ctx* ctx);  // vector_ops.cu: fold finished event pairs into prof_ms_cat / prof_cnt_cat
 // kernel categories of the in-region timing (fine grid only; multigrid levels reuse the kernels on coarser grids)
 enum { PROF_OP_PLAIN = 0, PROF_OP_SMOOTH = 1, PROF_OP_RESID = 2, PROF_FILTER = 3, PROF_SENS = 4, PROF_OC_VOLUMES = 5, PROF_PROLONG = 6,
-       PROF_RESTRICT = 7, PROF_MG_UPDATE_FIRST = 8, PROF_MG_DIRECTION = 9, PROF_NCAT = 10 };
+       PROF_RESTRICT = 7, PROF_MG_UPDATE_FIRST = 8, PROF_MG_DIRECTION = 9, PROF_UM_MATVEC = 10, PROF_NCAT = 11 };
 // bracket the launches between PROF_BEGIN and PROF_END with an event pair on the context's stream while profiling is on
 #define PROF_BEGIN(ctx, cat, cond)                                                                         \
     const bool _prof_timed = (ctx)->prof_on && (cond) && 2 * (ctx)->prof_n + 1 < (int)(ctx)->prof_ev.size(); \
@@ -199,6 +199,7 @@ int hex8_upload_constants(esimp_ctx* ctx);
 void hex8_forget_ctx(const esimp_ctx* ctx);
 void filter_forget_ctx(const esimp_ctx* ctx);
 void post_forget_ctx(const esimp_ctx* ctx);
+void um_forget_ctx(const esimp_ctx* ctx);
 // post_load.cu
 int body_force_into(esimp_ctx* ctx, const double* d_dens, double base, const double b[3], const double* d_fload, double* d_out);
 int body_force_refresh_rhs(esimp_ctx* ctx);  // d_f = d_fload + body(d_phys) when the body force is on

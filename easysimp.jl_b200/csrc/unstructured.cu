@@ -10,6 +10,7 @@
 // scatters with plain stores (race free by construction, deterministic).  Per-cell data is stored
 // colour-sorted and entry-major ([entry][cell]) so that a warp reads consecutive cells coalesced.
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <numeric>
@@ -39,6 +40,81 @@ __global__ void __launch_bounds__(128) k_um_matvec(long long s0, long long s1, l
         int d = celldofs[(long long)r * ncell + s];
         y[d] += Ee * acc;  // no other cell of this colour touches dof d
     }
+}
+
+// The same operator for general hexahedra WITHOUT the stored element matrices: K_e u_e = sum over the 2x2x2 Gauss points of
+// B' D B u_e detJ, rebuilt from the 8 node coordinates of the cell (FiniteElementAnalysis.jl:174-193 applied to u instead of
+// assembled).  24 coordinates (192 B) per cell per apply instead of the 576 entries of K_e (4.6 KB): the streamed variant is
+// bandwidth bound on exactly that array, this one is FP64 bound (~2.8 k flop per cell).  Reference gradients dN_a/dxi at the
+// Gauss points come from constant memory.
+__constant__ double c_um_dN[8][8][3];  // [gauss point][node][d/dxi_d] on the reference cube, VTK node order
+__global__ void __launch_bounds__(128) k_um_matvec_hex_geom(long long s0, long long s1, long long ncell, const int* __restrict__ order,
+                                                           const int* __restrict__ celldofs, const double* __restrict__ xcell,
+                                                           const double* __restrict__ E, const uint8_t* __restrict__ mask, double lam0,
+                                                           double mu0, const double* __restrict__ u, double* __restrict__ y) {
+    long long s = s0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= s1) return;
+    double x[8][3], ue[8][3], fe[8][3];
+    int dofs[24];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const int l = 3 * a + c;
+            x[a][c] = xcell[(long long)l * ncell + s];
+            dofs[l] = celldofs[(long long)l * ncell + s];
+            ue[a][c] = mask[dofs[l]] ? 0.0 : u[dofs[l]];
+            fe[a][c] = 0.0;
+        }
+#pragma unroll 1
+    for (int q = 0; q < 8; ++q) {
+        double J[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) J[c][d] = fma(x[a][c], c_um_dN[q][a][d], J[c][d]);
+        const double det = J[0][0] * (J[1][1] * J[2][2] - J[1][2] * J[2][1]) - J[0][1] * (J[1][0] * J[2][2] - J[1][2] * J[2][0]) +
+                           J[0][2] * (J[1][0] * J[2][1] - J[1][1] * J[2][0]);
+        const double id = 1.0 / det;
+        double Ji[3][3];
+        Ji[0][0] = (J[1][1] * J[2][2] - J[1][2] * J[2][1]) * id;
+        Ji[0][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * id;
+        Ji[0][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * id;
+        Ji[1][0] = (J[1][2] * J[2][0] - J[1][0] * J[2][2]) * id;
+        Ji[1][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * id;
+        Ji[1][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * id;
+        Ji[2][0] = (J[1][0] * J[2][1] - J[1][1] * J[2][0]) * id;
+        Ji[2][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * id;
+        Ji[2][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * id;
+        double g[8][3], H[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};  // g_a = grad N_a, H = grad u
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) g[a][c] = c_um_dN[q][a][0] * Ji[0][c] + c_um_dN[q][a][1] * Ji[1][c] + c_um_dN[q][a][2] * Ji[2][c];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int d = 0; d < 3; ++d) H[c][d] = fma(ue[a][c], g[a][d], H[c][d]);
+        }
+        // sigma = lam tr(eps) I + 2 mu eps, times the quadrature weight |det J| (unit weights)
+        const double w = fabs(det), tr = H[0][0] + H[1][1] + H[2][2];
+        double S[3][3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int d = 0; d < 3; ++d) S[c][d] = w * (mu0 * (H[c][d] + H[d][c]) + (c == d ? lam0 * tr : 0.0));
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) fe[a][c] += S[c][0] * g[a][0] + S[c][1] * g[a][1] + S[c][2] * g[a][2];
+    }
+    const double Ee = E[order[s]];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) y[dofs[3 * a + c]] += Ee * fe[a][c];  // no other cell of this colour touches these dofs
 }
 
 template <int ND>
@@ -240,17 +316,52 @@ int um_build(esimp_ctx* ctx, int celltype, int64_t n_cells, int64_t n_nodes, con
     return ESIMP_OK;
 }
 
+static const esimp_ctx* g_um_dn_owner = nullptr;
+static int um_upload_reference_gradients(esimp_ctx* ctx) {
+    if (g_um_dn_owner == ctx) return ESIMP_OK;
+    static const double R[8][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {1, 1, 1}, {-1, 1, 1}};
+    double dN[8][8][3];
+    const double gp = 1.0 / sqrt(3.0);
+    for (int q = 0; q < 8; ++q) {  // QuadratureRule{RefHexahedron}(2): first coordinate fastest
+        const double xi[3] = {(q & 1) ? gp : -gp, (q & 2) ? gp : -gp, (q & 4) ? gp : -gp};
+        for (int a = 0; a < 8; ++a) {
+            const double f0 = 1 + R[a][0] * xi[0], f1 = 1 + R[a][1] * xi[1], f2 = 1 + R[a][2] * xi[2];
+            dN[q][a][0] = 0.125 * R[a][0] * f1 * f2;
+            dN[q][a][1] = 0.125 * f0 * R[a][1] * f2;
+            dN[q][a][2] = 0.125 * f0 * f1 * R[a][2];
+        }
+    }
+    ESIMP_CUDA(cudaMemcpyToSymbolAsync(c_um_dN, dN, sizeof(dN), 0, cudaMemcpyHostToDevice, ctx->stream));
+    ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));  // dN is a stack array
+    g_um_dn_owner = ctx;
+    return ESIMP_OK;
+}
+void um_forget_ctx(const esimp_ctx* ctx) {
+    if (g_um_dn_owner == ctx) g_um_dn_owner = nullptr;
+}
+
 template <int ND>
 static int um_matvec_t(esimp_ctx* ctx, const double* d_in, double* d_out) {
     const UnstructuredMesh& um = ctx->um;
+    // hexahedra: K_e u_e from the node coordinates (ESIMP_UM_STREAM_KE=1 keeps the stored-matrix kernel for comparison)
+    static const bool stream_ke = getenv("ESIMP_UM_STREAM_KE") && atoi(getenv("ESIMP_UM_STREAM_KE")) == 1;
+    const bool geom = ND == 24 && !stream_ke;
+    if (geom) ESIMP_TRY(um_upload_reference_gradients(ctx));
+    const double nu = ctx->prm.nu, lam0 = nu / ((1 + nu) * (1 - 2 * nu)), mu0 = 1.0 / (2 * (1 + nu));
+    PROF_BEGIN(ctx, PROF_UM_MATVEC, true)
     ESIMP_CUDA(cudaMemsetAsync(d_out, 0, sizeof(double) * um.n_dofs, ctx->stream));
     for (int c = 0; c < um.n_colors; ++c) {
         long long s0 = um.color_ptr[c], s1 = um.color_ptr[c + 1];
         if (s1 == s0) continue;
-        k_um_matvec<ND><<<(unsigned)((s1 - s0 + 127) / 128), 128, 0, ctx->stream>>>(s0, s1, um.n_cells, um.d_order, um.d_celldofs,
-                                                                                    um.d_ke, ctx->d_E, ctx->d_mask, d_in, d_out);
+        if (geom)
+            k_um_matvec_hex_geom<<<(unsigned)((s1 - s0 + 127) / 128), 128, 0, ctx->stream>>>(s0, s1, um.n_cells, um.d_order, um.d_celldofs,
+                                                                                             um.d_xcell, ctx->d_E, ctx->d_mask, lam0, mu0, d_in, d_out);
+        else
+            k_um_matvec<ND><<<(unsigned)((s1 - s0 + 127) / 128), 128, 0, ctx->stream>>>(s0, s1, um.n_cells, um.d_order, um.d_celldofs,
+                                                                                        um.d_ke, ctx->d_E, ctx->d_mask, d_in, d_out);
         ctx->launches++;
     }
+    PROF_END(ctx)
     ESIMP_CUDA(cudaGetLastError());
     return ESIMP_OK;
 }

@@ -374,7 +374,7 @@ class Context:
         return ms.value, n.value
 
     PROF_NAMES = ["operator_plain_dot", "operator_smoother", "operator_residual", "filter_stencil", "sens_energy", "oc_volumes",
-                  "prolong_fine", "restrict_fine", "mg_update_first", "mg_direction"]
+                  "prolong_fine", "restrict_fine", "mg_update_first", "mg_direction", "um_matvec"]
 
     def profile_kernels(self):
         """{category: (summed kernel ms, launches)} of the in-region CUDA-event timing (esimp_profile_kernels)"""

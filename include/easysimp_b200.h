@@ -230,7 +230,8 @@ int esimp_profile_operator_all(esimp_ctx* ctx, double* ms_sum_all, int64_t* coun
 /* the same clock per kernel category, fine grid only (sum of kernel milliseconds and number of launches since
  * esimp_profile_enable): 0 operator plain / plain + dot, 1 operator with the smoother step fused in, 2 operator residual
  * mode, 3 filter stencil, 4 sensitivities + energy, 5 OC candidate volumes, 6 prolongation onto the fine grid,
- * 7 restriction of the fine residual, 8 first smoother step fused with the CG update, 9 CG direction update.
+ * 7 restriction of the fine residual, 8 first smoother step fused with the CG update, 9 CG direction update,
+ * 10 one whole coloured gather-scatter operator apply on an imported mesh (memset + one launch per colour).
  * n <= 16 entries are written. */
 int esimp_profile_kernels(esimp_ctx* ctx, int n, double* ms_sum, int64_t* count);
 /* number of kernels this context has launched so far */

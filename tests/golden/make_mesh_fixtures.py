@@ -1,4 +1,4 @@
-"""Convert the reference's imported-mesh test inputs (data/cantilever_beam.vtu, data/Wheel_3d_coarse.msh)
+"""Convert the reference's imported-mesh test inputs (data/cantilever_beam.vtu, data/Wheel_3d_coarse.msh, data/stul14.vtu, data/stul15.vtu)
 into compact .npz fixtures: /root/reference does not exist on the GPU box.  Only derived arrays
 (point coordinates + connectivity) are stored, no reference source.  Also extracts the one numeric OUTPUT the
 reference ships: the `density` cell field of data/cantilever_beam_opt.vtu (a 60x20x4 cantilever optimised by an
@@ -23,6 +23,10 @@ np.savez_compressed(OUT / "mesh_cantilever_beam_hex.npz", points=pts, cells=cell
 pts, cells = read_msh41(REF / "Wheel_3d_coarse.msh")
 print("Wheel_3d_coarse.msh", pts.shape, cells.shape, cells.min(), cells.max())
 np.savez_compressed(OUT / "mesh_wheel_coarse_tet.npz", points=pts, cells=cells.astype(np.int32))
+for name in ("stul14", "stul15"):  # general hexes: example 04's gripper (stul14) and its refinement (stul15, the c3 bench workload)
+    pts, cells = read_vtu(REF / f"{name}.vtu")
+    print(f"{name}.vtu", pts.shape, cells.shape)
+    np.savez_compressed(OUT / f"mesh_{name}_hex.npz", points=pts, cells=cells.astype(np.int32))
 pts, cells = read_vtu(REF / "cantilever_beam_opt.vtu")
 rho = read_vtu_arrays(REF / "cantilever_beam_opt.vtu")["density"].astype(np.float64)
 c = pts[cells].mean(axis=1)  # unit cubes: centroid (i+.5, j+.5, k+.5)

@@ -163,3 +163,56 @@ def test_host_api_on_imported_tets(golden_dir):
     assert np.max(np.abs(np.array(res.energy_history) - e_ref) / e_ref) < 1e-6
     assert np.abs(res.densities - ref["densities"]).max() < 1e-3
     K.ctx.close()
+
+
+def gripper_problem(golden_dir, name="mesh_stul14_hex"):
+    """test/Examples/04_gripper_complex.jl:36-226 on data/stul14.vtu without the body force: fixed circle on the mounting
+    surface, symmetry plane x = 0 (x component only), 13 N on the legs plane z = -90, 0.5 N on the camera ring"""
+    g = fixture_mesh(golden_dir, name)
+    dofs = o.distribute_dofs(g)
+    fixed = sorted(o.select_nodes_by_circle(g, [0.0, 75.0, 115.0], [0.0, -1.0, 0.0], 16.11, 1e-3))
+    sym = sorted(o.select_nodes_by_plane(g, [0.0, 0.0, 0.0], [1.0, 0.0, 0.0], 1e-3))
+    leg = sorted(o.select_nodes_by_plane(g, [0.0, 0.0, -90.0], [0.0, 0.0, 1.0], 1.0))
+    cam = sorted(o.select_nodes_by_circle(g, [0.0, 0.0, 5.0], [0.0, 0.0, 1.0], 21.5, 1e-3))
+    pres = np.unique(np.concatenate([dofs[np.array(fixed)].ravel(), dofs[np.array(sym), 0]]))
+    f = o.apply_point_load(np.zeros(int(dofs.max()) + 1), dofs, leg, [0.0, 0.0, -13000.0])
+    f = o.apply_point_load(f, dofs, cam, [0.0, 0.0, -500.0])
+    return g, dofs, pres, f, (len(fixed), len(sym), len(leg), len(cam))
+
+
+def test_gripper_stul14_first_iteration(gpu_ctx_factory, golden_dir):
+    """BASELINE config 3 on the reference's largest scripted mesh (16 490 general hexes, 61 626 dofs), example-04 material
+    (E0 = 2400, nu = 0.35, Emin = 1e-6, vf = 0.3, r = 1.5): operator, diagonal and sensitivities against the oracle, the
+    Jacobi-PCG solve against the oracle's CG, and one whole SIMP iteration (compliance 1e-6, design 1e-3)."""
+    g, dofs, pres, f, counts = gripper_problem(golden_dir)
+    assert counts == (27, 798, 96, 93)
+    nd = int(dofs.max()) + 1
+    E0, nu, Emin, vf = 2.4e3, 0.35, 1e-6, 0.3
+    V = o.element_volumes(g)
+    fc = o.create_filter_cache(g, 1.5, V)
+    ctx = make_ctx(gpu_ctx_factory, g, dofs, pres, E0=E0, nu=nu, Emin=Emin, volume_fraction=vf, filter_radius=fc.radius, pcg_rtol=1e-10,
+                   pcg_check_every=50)
+    ctx.set_load(f)
+    ctx.filter_build_csr(fc.rowptr, fc.col, fc.centers, V, fc.radius)
+    rho = np.full(g.n_cells, vf)
+    ctx.set_density(rho)
+    k0 = o.unit_element_matrices(g, nu, 1.0)
+    E = o.simp_modulus(rho, E0, Emin, 3.0)
+    d = o.operator_diagonal(g, dofs, E, k0)
+    m = float(np.mean(d))
+    u = np.random.default_rng(2).standard_normal(nd)
+    assert relmax(ctx.matvec(u), o.operator_apply(g, dofs, E, k0, pres, u, m)) < 1e-12
+    ug, iters, relres, st = ctx.solve()
+    Kbc, fbc, _ = o.apply_dirichlet(o.assemble_stiffness(g, dofs, E, k0), f.copy(), pres)
+    u_ref, _ = o.solve_pcg(Kbc, fbc, rtol=1e-12)
+    assert st == 0 and relmax(ug, u_ref) < 1e-6 and np.all(ug[pres] == 0)
+    # one SIMP iteration of the library against the oracle's stages on the oracle's displacement
+    energy_ref = 0.5 * float(u_ref @ (Kbc @ u_ref))
+    dc_ref = o.sensitivities(g, dofs, rho, u_ref, E0, Emin, nu, 3.0, k0)
+    dcf_ref = o.filter_sensitivity(fc, rho, dc_ref)
+    new_ref, lam_ref, _, _ = o.optimality_criteria_update(rho, dcf_ref, V / V.sum(), vf, V.sum(), V, 0.2, 0.5, fc, False)
+    ctx.init_design(None)
+    s = ctx.iterate()
+    assert abs(s.energy - energy_ref) / energy_ref < 1e-6 and abs(s.lam - lam_ref) / lam_ref < 1e-5
+    assert np.abs(ctx.get_design() - new_ref).max() < 1e-3
+    ctx.close()
