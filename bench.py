@@ -519,6 +519,16 @@ def run_b200(args):
                "phases_ms_per_step": {k: float(np.mean([getattr(s, k) for s in timed])) for k in ("ms_filter", "ms_solve", "ms_sens", "ms_oc")},
                "history": [{"energy": s.energy, "change": s.change, "pcg_iters": s.pcg_iters, "pcg_relres": s.pcg_relres, "oc_steps": s.oc_steps}
                            for s in stats + timed]}
+        if world > 1:
+            # rank 0's clocks of what the slab partition adds (CUDA events on the library's stream; a halo / allreduce time
+            # includes waiting for the slower neighbour) and two host clocks of the PCG loop, all per SIMP step
+            def per_step(k):
+                ms, cnt = kernels.get(k, (0.0, 0))
+                return {"ms_per_step": ms / args.steps, "count_per_step": cnt / args.steps, "avg_ms": ms / cnt if cnt else None}
+            out["multi_gpu_breakdown"] = {k: per_step(k) for k in ("comm_halo", "comm_allreduce_scalars", "comm_level_sum", "mg_below_fine",
+                                                                   "host_pcg_wall", "host_pcg_wait", "operator_plain_dot",
+                                                                   "operator_smoother", "operator_residual", "mg_update_first",
+                                                                   "mg_direction", "prolong_fine", "restrict_fine")}
         if world == 1 and not args.no_cpu_baseline:
             # the CPU port is Jacobi-PCG: scale its sample with ITS iteration count on the same SIMP iterations (measured once with
             # the same Jacobi-PCG on the GPU, bench_calibration.json), not with this arm's multigrid count

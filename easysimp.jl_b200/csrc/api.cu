@@ -156,6 +156,8 @@ int esimp_destroy(esimp_ctx* ctx) {
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : ctx->prof_ev) cudaEventDestroy(e);
+    for (auto& e : ctx->prof_coarse_ev)
+        if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return ESIMP_OK;
@@ -802,9 +804,10 @@ int esimp_profile_enable(esimp_ctx* ctx, int on) {
         ctx->prof_ev.resize(2 * 4096);
         ctx->prof_tag.assign(4096, 0);
         for (auto& e : ctx->prof_ev) ESIMP_CUDA(cudaEventCreate(&e));
+        for (auto& e : ctx->prof_coarse_ev) ESIMP_CUDA(cudaEventCreate(&e));
     }
     ctx->prof_on = on != 0;
-    for (int c = 0; c < 16; ++c) {
+    for (int c = 0; c < PROF_NCAT; ++c) {
         ctx->prof_ms_cat[c] = 0.0;
         ctx->prof_cnt_cat[c] = 0;
     }
@@ -838,7 +841,7 @@ int esimp_profile_operator_all(esimp_ctx* ctx, double* ms_sum_all, int64_t* coun
 
 int esimp_profile_kernels(esimp_ctx* ctx, int n, double* ms_sum, int64_t* count) {
     CHECK_CTX();
-    if (n < 0 || n > 16 || !ms_sum || !count) return esimp_fail(ctx, ESIMP_ERR_ARG, "bad arguments");
+    if (n < 0 || n > PROF_NCAT || !ms_sum || !count) return esimp_fail(ctx, ESIMP_ERR_ARG, "bad arguments");
     ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));
     ESIMP_TRY(prof_collect(ctx));
     for (int c = 0; c < n; ++c) {

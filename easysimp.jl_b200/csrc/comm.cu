@@ -101,8 +101,10 @@ void comm_destroy(esimp_ctx* ctx) {
 
 int comm_allreduce(esimp_ctx* ctx, double* d_buf, long long n, bool is_max) {
     if (ctx->nranks <= 1) return ESIMP_OK;
+    PROF_BEGIN(ctx, n <= 16 ? PROF_COMM_ALLREDUCE : PROF_COMM_LEVELSUM, true)
     ESIMP_NCCL(g_nccl.AllReduce(d_buf, d_buf, (size_t)n, ncclDouble, is_max ? ncclMax : ncclSum, (ncclComm_t)ctx->nccl_comm,
                                 ctx->stream));
+    PROF_END(ctx)
     return ESIMP_OK;
 }
 
@@ -112,6 +114,7 @@ int comm_halo_nodes_lv(esimp_ctx* ctx, const GridDev& g, int own_p0, int own_p1,
     if (ctx->nranks <= 1) return ESIMP_OK;
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
     const size_t np = (size_t)3 * g.plane;
+    PROF_BEGIN(ctx, PROF_COMM_HALO, true)
     ESIMP_NCCL(g_nccl.GroupStart());
     if (has_left) {
         ESIMP_NCCL(g_nccl.Send(v + (size_t)own_p0 * np, np, ncclDouble, ctx->rank - 1, comm, ctx->stream));
@@ -122,6 +125,7 @@ int comm_halo_nodes_lv(esimp_ctx* ctx, const GridDev& g, int own_p0, int own_p1,
         ESIMP_NCCL(g_nccl.Recv(v + (size_t)(g.NPX - 1) * np, np, ncclDouble, ctx->rank + 1, comm, ctx->stream));
     }
     ESIMP_NCCL(g_nccl.GroupEnd());
+    PROF_END(ctx)
     return ESIMP_OK;
 }
 int comm_allreduce_f32(esimp_ctx* ctx, float* d_buf, long long n) {

@@ -161,13 +161,19 @@ struct esimp_ctx {
     std::vector<cudaEvent_t> prof_ev;
     std::vector<uint8_t> prof_tag;
     int prof_n = 0;
-    double prof_ms_cat[16] = {0};    // summed kernel time per category (PROF_* below)
-    int64_t prof_cnt_cat[16] = {0};
+    double prof_ms_cat[24] = {0};    // summed kernel time per category (PROF_* below)
+    int64_t prof_cnt_cat[24] = {0};
+    cudaEvent_t prof_coarse_ev[2]{};  // one V-cycle's levels >= 1 (PROF_MG_COARSE): own pair, it encloses other categories
+    bool prof_coarse_pending = false;
 };
 int prof_collect(esimp_ctx* ctx);  // vector_ops.cu: fold finished event pairs into prof_ms_cat / prof_cnt_cat
 // kernel categories of the in-region timing (fine grid only; multigrid levels reuse the kernels on coarser grids)
 enum { PROF_OP_PLAIN = 0, PROF_OP_SMOOTH = 1, PROF_OP_RESID = 2, PROF_FILTER = 3, PROF_SENS = 4, PROF_OC_VOLUMES = 5, PROF_PROLONG = 6,
-       PROF_RESTRICT = 7, PROF_MG_UPDATE_FIRST = 8, PROF_MG_DIRECTION = 9, PROF_UM_MATVEC = 10, PROF_NCAT = 11 };
+       PROF_RESTRICT = 7, PROF_MG_UPDATE_FIRST = 8, PROF_MG_DIRECTION = 9, PROF_UM_MATVEC = 10,
+       // slab partition: neighbour plane exchange, scalar allreduces, the level-sum allreduce at the distributed -> replicated
+       // transition, everything below level 0 of one V-cycle (restriction to prolongation), and two HOST clocks of the PCG loop
+       // (ms blocked in the per-iteration scalar fetch; ms of the whole solve)
+       PROF_COMM_HALO = 11, PROF_COMM_ALLREDUCE = 12, PROF_COMM_LEVELSUM = 13, PROF_MG_COARSE = 14, PROF_HOST_PCG = 15, PROF_HOST_WAIT = 16, PROF_NCAT = 17 };
 // bracket the launches between PROF_BEGIN and PROF_END with an event pair on the context's stream while profiling is on
 #define PROF_BEGIN(ctx, cat, cond)                                                                         \
     const bool _prof_timed = (ctx)->prof_on && (cond) && 2 * (ctx)->prof_n + 1 < (int)(ctx)->prof_ev.size(); \

@@ -27,6 +27,8 @@
 
 #include <algorithm>
 
+#include <chrono>
+
 #include "ctx.cuh"
 
 #define LAUNCH_STREAM(kern, ...)                                        \
@@ -554,6 +556,9 @@ static int mg_vcycle(esimp_ctx* ctx, int l, bool first_done = false, int dot_slo
         ESIMP_TRY(mg_apply(ctx, L, L.d_z, L.d_q));
         LAUNCH_STREAM(k_residual, L.d_r, L.d_q, L.own_dof0, L.own_dof1);
     }
+    // PROF_MG_COARSE: from the exchange of the fine residual to the end of the prolongation, one pair per V-cycle
+    const bool time_coarse = l == 0 && ctx->prof_on && !ctx->prof_coarse_pending && ctx->prof_coarse_ev[0];
+    if (time_coarse) cudaEventRecord(ctx->prof_coarse_ev[0], ctx->stream);
     if (ctx->nranks > 1) ESIMP_TRY(comm_halo_nodes_lv(ctx, L.vw.g, L.vw.own_p0, L.vw.own_p1, L.has_left, L.has_right, L.d_q));
     if (C.replicated && !L.replicated) {
         // distributed -> replicated: restrict onto the coarse planes I whose fine plane 2I this rank owns (their
@@ -594,6 +599,10 @@ static int mg_vcycle(esimp_ctx* ctx, int l, bool first_done = false, int dot_slo
         ctx->launches++;
         ESIMP_CUDA(cudaGetLastError());
     }
+    if (time_coarse) {
+        cudaEventRecord(ctx->prof_coarse_ev[1], ctx->stream);
+        ctx->prof_coarse_pending = true;
+    }
     return mg_smooth(ctx, L, ctx->mg_nu, false, false, dot_slot, dot_done);
 }
 
@@ -606,8 +615,23 @@ __global__ void k_dot2(const double* __restrict__ a, const double* __restrict__ 
 }
 
 // CG preconditioned with one V-cycle per iteration.  Same contract as pcg_solve (vector_ops.cu).
+struct HostPcgClock {  // PROF_HOST_PCG / PROF_HOST_WAIT: wall time of the solve and of the blocking scalar fetches
+    esimp_ctx* ctx;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double wait_ms = 0.0;
+    int fetches = 0;
+    explicit HostPcgClock(esimp_ctx* c) : ctx(c) {}
+    ~HostPcgClock() {
+        if (!ctx->prof_on) return;
+        ctx->prof_ms_cat[PROF_HOST_PCG] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        ctx->prof_cnt_cat[PROF_HOST_PCG] += 1;
+        ctx->prof_ms_cat[PROF_HOST_WAIT] += wait_ms;
+        ctx->prof_cnt_cat[PROF_HOST_WAIT] += fetches;
+    }
+};
 int pcg_solve_mg(esimp_ctx* ctx, int* iters, double* relres) {
     if (ctx->mg.empty()) return esimp_fail(ctx, ESIMP_ERR_STATE, "multigrid hierarchy not built");
+    HostPcgClock clock(ctx);
     MGLevel& L0 = ctx->mg[0];
     const long long i0 = ctx->own_dof0, i1 = ctx->own_dof1;
     double* S = ctx->d_scal;
@@ -659,7 +683,12 @@ int pcg_solve_mg(esimp_ctx* ctx, int* iters, double* relres) {
             ESIMP_TRY(allreduce_scalars(ctx, SC_RR0, 1, false));
         }
         ++it;
-        ESIMP_TRY(fetch_scalars(ctx));
+        {
+            const auto w0 = std::chrono::steady_clock::now();
+            ESIMP_TRY(fetch_scalars(ctx));
+            clock.wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+            clock.fetches++;
+        }
         rr = ctx->h_scal[SC_RR0];
         if (getenv("ESIMP_MG_DEBUG") && ctx->rank == 0)
             fprintf(stderr, "[mg] it %d rr %.6e pq %.6e rz %.6e\n", it, rr, ctx->h_scal[SC_PQ], ctx->h_scal[RZ[cur]]);

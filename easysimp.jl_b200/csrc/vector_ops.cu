@@ -113,12 +113,20 @@ int prof_collect(esimp_ctx* ctx) {
     for (int i = 0; i < ctx->prof_n; ++i) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->prof_ev[2 * i], ctx->prof_ev[2 * i + 1]) == cudaSuccess) {
-            const int cat = ctx->prof_tag[i] < 16 ? ctx->prof_tag[i] : 15;
+            const int cat = ctx->prof_tag[i] < PROF_NCAT ? ctx->prof_tag[i] : PROF_NCAT - 1;
             ctx->prof_ms_cat[cat] += ms;
             ctx->prof_cnt_cat[cat]++;
         }
     }
     ctx->prof_n = 0;
+    if (ctx->prof_coarse_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->prof_coarse_ev[0], ctx->prof_coarse_ev[1]) == cudaSuccess) {
+            ctx->prof_ms_cat[PROF_MG_COARSE] += ms;
+            ctx->prof_cnt_cat[PROF_MG_COARSE]++;
+        }
+        ctx->prof_coarse_pending = false;
+    }
     return ESIMP_OK;
 }
 int allreduce_scalars(esimp_ctx* ctx, int slot0, int n, bool is_max) {

@@ -374,7 +374,8 @@ class Context:
         return ms.value, n.value
 
     PROF_NAMES = ["operator_plain_dot", "operator_smoother", "operator_residual", "filter_stencil", "sens_energy", "oc_volumes",
-                  "prolong_fine", "restrict_fine", "mg_update_first", "mg_direction", "um_matvec"]
+                  "prolong_fine", "restrict_fine", "mg_update_first", "mg_direction", "um_matvec", "comm_halo", "comm_allreduce_scalars",
+                  "comm_level_sum", "mg_below_fine", "host_pcg_wall", "host_pcg_wait"]
 
     def profile_kernels(self):
         """{category: (summed kernel ms, launches)} of the in-region CUDA-event timing (esimp_profile_kernels)"""
