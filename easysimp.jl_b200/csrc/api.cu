@@ -122,6 +122,7 @@ int esimp_create(esimp_ctx** out, int device) {
     if (const char* e = getenv("ESIMP_MG_MIN_LAYERS")) ctx->mg_min_layers = std::max(1, atoi(e));
     if (const char* e = getenv("ESIMP_MG_REPLICATE")) ctx->mg_replicate = atoi(e);
     if (const char* e = getenv("ESIMP_MG_REPLICATE_CELLS")) ctx->mg_replicate_cells = atoll(e);
+    if (const char* e = getenv("ESIMP_PCG_LAG")) ctx->mg_lag = atoi(e);
     auto bail = [&](const char* what) {
         std::string msg = std::string(what) + ": " + cudaGetErrorString(cudaGetLastError());
         esimp_destroy(ctx);  // frees whatever was created so far
@@ -132,10 +133,11 @@ int esimp_create(esimp_ctx** out, int device) {
     if (cudaMalloc(&ctx->d_partial, sizeof(double) * 16 * RED_BLOCKS) != cudaSuccess) return bail("cudaMalloc");
     if (cudaMalloc(&ctx->d_ticket, sizeof(unsigned int) * 8) != cudaSuccess) return bail("cudaMalloc");
     if (cudaMalloc(&ctx->d_scal, sizeof(double) * N_SCAL) != cudaSuccess) return bail("cudaMalloc");
-    if (cudaMallocHost(&ctx->h_scal, sizeof(double) * N_SCAL) != cudaSuccess) return bail("cudaMallocHost");
+    if (cudaMallocHost(&ctx->h_scal, sizeof(double) * (N_SCAL + 2)) != cudaSuccess) return bail("cudaMallocHost");
     cudaMemset(ctx->d_ticket, 0, sizeof(unsigned int) * 8);
     cudaMemset(ctx->d_scal, 0, sizeof(double) * N_SCAL);
     for (auto& e : ctx->ev) cudaEventCreate(&e);
+    for (auto& e : ctx->lag_ev) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
     *out = ctx;
     return ESIMP_OK;
 }
@@ -156,6 +158,8 @@ int esimp_destroy(esimp_ctx* ctx) {
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : ctx->prof_ev) cudaEventDestroy(e);
+    for (auto& e : ctx->lag_ev)
+        if (e) cudaEventDestroy(e);
     for (auto& e : ctx->prof_coarse_ev)
         if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);

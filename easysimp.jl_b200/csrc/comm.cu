@@ -61,6 +61,25 @@ static int load_nccl(std::string& err) {
     return ESIMP_OK;
 }
 
+// inside ncclGroupStart / ncclGroupEnd: remember the first failure and carry on, so that the group is always closed
+#define ESIMP_NCCL_IN_GROUP(call)                                   \
+    do {                                                            \
+        ncclResult_t _r = (call);                                   \
+        if (_r != ncclSuccess && _grp_err == ncclSuccess) {         \
+            _grp_err = _r;                                          \
+            _grp_what = #call;                                      \
+        }                                                           \
+    } while (0)
+#define ESIMP_NCCL_GROUP_BEGIN()           \
+    ncclResult_t _grp_err = ncclSuccess;   \
+    const char* _grp_what = "";            \
+    ESIMP_NCCL(g_nccl.GroupStart())
+#define ESIMP_NCCL_GROUP_END()                                                                                        \
+    do {                                                                                                              \
+        ncclResult_t _e = g_nccl.GroupEnd();                                                                          \
+        if (_grp_err != ncclSuccess) return esimp_fail(ctx, ESIMP_ERR_NCCL, std::string(_grp_what) + ": " + g_nccl.GetErrorString(_grp_err)); \
+        if (_e != ncclSuccess) return esimp_fail(ctx, ESIMP_ERR_NCCL, std::string("ncclGroupEnd: ") + g_nccl.GetErrorString(_e));            \
+    } while (0)
 #define ESIMP_NCCL(call)                                                                                         \
     do {                                                                                                         \
         ncclResult_t _r = (call);                                                                                \
@@ -115,16 +134,16 @@ int comm_halo_nodes_lv(esimp_ctx* ctx, const GridDev& g, int own_p0, int own_p1,
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
     const size_t np = (size_t)3 * g.plane;
     PROF_BEGIN(ctx, PROF_COMM_HALO, true)
-    ESIMP_NCCL(g_nccl.GroupStart());
+    ESIMP_NCCL_GROUP_BEGIN();
     if (has_left) {
-        ESIMP_NCCL(g_nccl.Send(v + (size_t)own_p0 * np, np, ncclDouble, ctx->rank - 1, comm, ctx->stream));
-        ESIMP_NCCL(g_nccl.Recv(v, np, ncclDouble, ctx->rank - 1, comm, ctx->stream));
+        ESIMP_NCCL_IN_GROUP(g_nccl.Send(v + (size_t)own_p0 * np, np, ncclDouble, ctx->rank - 1, comm, ctx->stream));
+        ESIMP_NCCL_IN_GROUP(g_nccl.Recv(v, np, ncclDouble, ctx->rank - 1, comm, ctx->stream));
     }
     if (has_right) {
-        ESIMP_NCCL(g_nccl.Send(v + (size_t)(own_p1 - 1) * np, np, ncclDouble, ctx->rank + 1, comm, ctx->stream));
-        ESIMP_NCCL(g_nccl.Recv(v + (size_t)(g.NPX - 1) * np, np, ncclDouble, ctx->rank + 1, comm, ctx->stream));
+        ESIMP_NCCL_IN_GROUP(g_nccl.Send(v + (size_t)(own_p1 - 1) * np, np, ncclDouble, ctx->rank + 1, comm, ctx->stream));
+        ESIMP_NCCL_IN_GROUP(g_nccl.Recv(v + (size_t)(g.NPX - 1) * np, np, ncclDouble, ctx->rank + 1, comm, ctx->stream));
     }
-    ESIMP_NCCL(g_nccl.GroupEnd());
+    ESIMP_NCCL_GROUP_END();
     PROF_END(ctx)
     return ESIMP_OK;
 }
@@ -137,16 +156,16 @@ int comm_halo_nodes_lv_f32(esimp_ctx* ctx, const GridDev& g, int own_p0, int own
     if (ctx->nranks <= 1) return ESIMP_OK;
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
     const size_t np = (size_t)3 * g.plane;
-    ESIMP_NCCL(g_nccl.GroupStart());
+    ESIMP_NCCL_GROUP_BEGIN();
     if (has_left) {
-        ESIMP_NCCL(g_nccl.Send(v + (size_t)own_p0 * np, np, ncclFloat, ctx->rank - 1, comm, ctx->stream));
-        ESIMP_NCCL(g_nccl.Recv(v, np, ncclFloat, ctx->rank - 1, comm, ctx->stream));
+        ESIMP_NCCL_IN_GROUP(g_nccl.Send(v + (size_t)own_p0 * np, np, ncclFloat, ctx->rank - 1, comm, ctx->stream));
+        ESIMP_NCCL_IN_GROUP(g_nccl.Recv(v, np, ncclFloat, ctx->rank - 1, comm, ctx->stream));
     }
     if (has_right) {
-        ESIMP_NCCL(g_nccl.Send(v + (size_t)(own_p1 - 1) * np, np, ncclFloat, ctx->rank + 1, comm, ctx->stream));
-        ESIMP_NCCL(g_nccl.Recv(v + (size_t)(g.NPX - 1) * np, np, ncclFloat, ctx->rank + 1, comm, ctx->stream));
+        ESIMP_NCCL_IN_GROUP(g_nccl.Send(v + (size_t)(own_p1 - 1) * np, np, ncclFloat, ctx->rank + 1, comm, ctx->stream));
+        ESIMP_NCCL_IN_GROUP(g_nccl.Recv(v + (size_t)(g.NPX - 1) * np, np, ncclFloat, ctx->rank + 1, comm, ctx->stream));
     }
-    ESIMP_NCCL(g_nccl.GroupEnd());
+    ESIMP_NCCL_GROUP_END();
     return ESIMP_OK;
 }
 int comm_halo_nodes(esimp_ctx* ctx, double* v) {
@@ -158,16 +177,16 @@ int comm_halo_cells_lv(esimp_ctx* ctx, const GridDev& g, int own_e0, int own_e1,
     if (ctx->nranks <= 1) return ESIMP_OK;
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
     const size_t nl = (size_t)depth * g.eplane;
-    ESIMP_NCCL(g_nccl.GroupStart());
+    ESIMP_NCCL_GROUP_BEGIN();
     if (has_left) {
-        ESIMP_NCCL(g_nccl.Send(a + (size_t)own_e0 * g.eplane, nl, ncclDouble, ctx->rank - 1, comm, ctx->stream));
-        ESIMP_NCCL(g_nccl.Recv(a + (size_t)(own_e0 - depth) * g.eplane, nl, ncclDouble, ctx->rank - 1, comm, ctx->stream));
+        ESIMP_NCCL_IN_GROUP(g_nccl.Send(a + (size_t)own_e0 * g.eplane, nl, ncclDouble, ctx->rank - 1, comm, ctx->stream));
+        ESIMP_NCCL_IN_GROUP(g_nccl.Recv(a + (size_t)(own_e0 - depth) * g.eplane, nl, ncclDouble, ctx->rank - 1, comm, ctx->stream));
     }
     if (has_right) {
-        ESIMP_NCCL(g_nccl.Send(a + (size_t)(own_e1 - depth) * g.eplane, nl, ncclDouble, ctx->rank + 1, comm, ctx->stream));
-        ESIMP_NCCL(g_nccl.Recv(a + (size_t)own_e1 * g.eplane, nl, ncclDouble, ctx->rank + 1, comm, ctx->stream));
+        ESIMP_NCCL_IN_GROUP(g_nccl.Send(a + (size_t)(own_e1 - depth) * g.eplane, nl, ncclDouble, ctx->rank + 1, comm, ctx->stream));
+        ESIMP_NCCL_IN_GROUP(g_nccl.Recv(a + (size_t)own_e1 * g.eplane, nl, ncclDouble, ctx->rank + 1, comm, ctx->stream));
     }
-    ESIMP_NCCL(g_nccl.GroupEnd());
+    ESIMP_NCCL_GROUP_END();
     return ESIMP_OK;
 }
 int comm_halo_cells(esimp_ctx* ctx, double* a) {

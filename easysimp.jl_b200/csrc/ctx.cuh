@@ -118,6 +118,13 @@ struct esimp_ctx {
     int mg_min_layers = 1;  // multi-rank: stop coarsening when a rank would hold fewer cell layers than this
     int mg_nu = 2, mg_coarse_its = 16;  // tuned on 512x256x256 (scripts/mg_sweep.sh): nu 2, ratio 10 is the fastest
     double mg_ratio = 10.0;
+    // GMG-CG convergence poll: 0 = read <r,r> back after every iteration (the host waits for the device once per iteration),
+    // 1 = lagged: iteration k is enqueued before <r,r> of iteration k-1 is looked at, so the host runs one iteration ahead and the
+    // tiny coarse-level launches / NCCL calls never starve the device.  The iterate returned is the same (the deferred x update of
+    // the surplus iteration is never applied).  -1 = auto: lagged on multi-rank contexts only (on one B200 the fine-grid kernels are long enough for the host to keep ahead and
+    // the lagged poll measured 2 % slower); ESIMP_PCG_LAG = 0 / 1 forces it
+    int mg_lag = -1;
+    cudaEvent_t lag_ev[2]{};
 
     // element matrices (host copies; uploaded to __constant__ on demand)
     double K0[24 * 24];

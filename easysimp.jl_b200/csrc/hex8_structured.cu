@@ -286,8 +286,16 @@ static int make_map3(esimp_ctx* ctx, CUtensorMap* tm, const void* base, cuuint64
     if (!enc) return esimp_fail(ctx, ESIMP_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
     cuuint64_t dim[3] = {d0, d1, d2}, stride[2] = {s1 * 8, s2 * 8};
     cuuint32_t box[3] = {b0, b1, b2}, es[3] = {1, 1, 1};
+    // L2 promotion: the boxes are 256- / 272-byte row pieces that start 64-byte aligned, so a 256-byte promotion granule fetches
+    // up to twice the bytes from DRAM (ncu r2: 1.73 GB read per plain apply against 1.28 GB of box bytes; the smoother mode with
+    // its three operand boxes per plane went from 1.45 ms to 1.13 ms with 64-byte granules, 1.30 / 1.31 ms with 128 / none).
+    // ESIMP_TMA_PROMO = 0 .. 3 selects none / 64 / 128 / 256 bytes; default 64
+    static const int promo = getenv("ESIMP_TMA_PROMO") ? atoi(getenv("ESIMP_TMA_PROMO")) : 1;
+    const CUtensorMapL2promotion l2p = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                     : promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                     : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
     CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<void*>(base), dim, stride, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_NONE, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return esimp_fail(ctx, ESIMP_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
     return ESIMP_OK;
 }
@@ -449,9 +457,10 @@ int hex8_smooth_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, doubl
     fa.dmode = dmode;
     fa.write_d = write_d;
     fa.zprev = zprev;
-    // smoother modes: 48 B/dof make them memory-latency bound, where the round-1 kernel's 16 warps per SM win (r2, 512x256x256:
-    // 1.29 ms vs 1.39 ms for the sweep kernel's 8 warps).  ESIMP_SWEEP_SMOOTH=1 (or naming the variant) selects the sweep kernel.
-    static const int sweep_smooth = getenv("ESIMP_SWEEP_SMOOTH") ? atoi(getenv("ESIMP_SWEEP_SMOOTH")) : 0;
+    // smoother modes: with 256-byte TMA promotion the sweep kernel's operand boxes over-fetched (1.39 - 1.45 ms against 1.29 ms for the
+    // round-1 kernel at 512x256x256); with 64-byte granules it is the faster one (inside the SIMP step: 0.90 ms against 1.15 ms per
+    // smoother launch, profiles/README.md).  ESIMP_SWEEP_SMOOTH=0 goes back to the round-1 kernel for these modes.
+    static const int sweep_smooth = getenv("ESIMP_SWEEP_SMOOTH") ? atoi(getenv("ESIMP_SWEEP_SMOOTH")) : 1;
     if ((sweep_smooth || ctx->prm.matvec_variant == ESIMP_MATVEC_SWEEP) && hex8_sweep_eligible(ctx, vw)) {
         const bool fine = vw.E == ctx->d_E;
         return dot_slot >= 0 ? launch_sweep<FUSE_SMOOTH_DOT>(ctx, vw, fine, z_in, z_out, dot_slot, fa)

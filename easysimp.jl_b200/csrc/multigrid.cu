@@ -59,21 +59,25 @@ __global__ void k_restrict_E(GridDev gf, GridDev gc, int ce0, int ce1, const dou
 }
 
 // r_c = P' res_f on the owned coarse nodes (27-point full weighting), 0 on prescribed coarse dofs
-__global__ void __launch_bounds__(256) k_restrict(GridDev gf, GridDev gc, int cp0, int cp1, const double* __restrict__ resf,
+// coarse planes a thread marches through (one extra fine plane is read per chunk): long chunks where bandwidth counts, single
+// planes on the small levels where only the latency of the launch does
+static inline int restrict_chunk(long long coarse_dofs) { return coarse_dofs >= 400000 ? 8 : 1; }
+__global__ void __launch_bounds__(256) k_restrict(GridDev gf, GridDev gc, int cp0, int cp1, int chunk, const double* __restrict__ resf,
                                                   const uint8_t* __restrict__ maskc, double* __restrict__ rc) {
-    // One thread per coarse dof: blockIdx.y walks the (coarse plane, component) pairs, the x dimension the (J, K) positions of a
-    // plane incl. the row pads (32-bit index arithmetic only), lanes along K.  Along z the three fine values 2K-1, 2K, 2K+1 come
-    // from ONE aligned 16-byte load (2K, 2K+1) plus the second half of the left neighbour lane's pair (the pad entries behind a
-    // fine row are zero, so 2K+1 past the last node contributes nothing): 9 coalesced 16-byte loads per node instead of 27
-    // stride-2 scalar ones.
+    // One thread per coarse (J, K) position and component; it MARCHES along x through a chunk of coarse planes (blockIdx.y walks the
+    // (chunk, component) pairs), so every fine plane is read once: the y-z weighted sum of the odd fine plane 2I+1 is carried from
+    // coarse plane I to I+1 (6 loads of 16 bytes per coarse dof instead of 9; the round-2 launch list had the 9-load version at
+    // 0.44 ms = 0.32 of the HBM roofline on the fine grid).  The x dimension of the grid covers the (J, K) positions of a plane incl.
+    // the row pads (32-bit index arithmetic only), lanes along K.  Along z the three fine values 2K-1, 2K, 2K+1 come from ONE aligned
+    // 16-byte load (2K, 2K+1) plus the second half of the left neighbour lane's pair (the pad entries behind a fine row are zero, so
+    // 2K+1 past the last node contributes nothing).
     const int nJK = (gc.ny + 1) * gc.nzp;
     const int nJK_round = (nJK + 31) / 32 * 32;  // whole warps: the shuffles need every lane
     const int lane = threadIdx.x & 31;
-    for (int pc = blockIdx.y; pc < (cp1 - cp0) * 3; pc += gridDim.y) {
-        const int Lp = cp0 + pc / 3, c = pc % 3;
-        const int Gf = 2 * (gc.gp0 + Lp), lpf = Gf - gf.gp0;
-        const uint8_t* __restrict__ mrow = maskc + (long long)Lp * gc.plane;
-        double* __restrict__ out = rc + (long long)(Lp * 3 + c) * gc.plane;
+    const int nchunk = (cp1 - cp0 + chunk - 1) / chunk;
+    for (int pc = blockIdx.y; pc < nchunk * 3; pc += gridDim.y) {
+        const int c = pc % 3;
+        const int L0 = cp0 + (pc / 3) * chunk, L1 = min(L0 + chunk, cp1);
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nJK_round; i += gridDim.x * blockDim.x) {
             const bool in_range = i < nJK;
             const int id = in_range ? i : nJK - 1;
@@ -81,11 +85,11 @@ __global__ void __launch_bounds__(256) k_restrict(GridDev gf, GridDev gc, int cp
             const bool node = in_range && K <= gc.nz;     // pad entries of the coarse rows stay zero
             const bool left_in_lane = lane > 0 && K > 0;  // lane - 1 holds (J, K - 1) of the same row
             const int kf = 2 * (K <= gc.nz ? K : gc.nz);  // pad threads read a valid address, their result is dropped
-            double acc = 0.0;
-#pragma unroll
-            for (int dx = -1; dx <= 1; ++dx) {
-                const bool xok = !(Gf + dx < 0 || Gf + dx > gf.nx || lpf + dx < 0 || lpf + dx >= gf.NPX);
-                const double* __restrict__ fplane = resf + (long long)((xok ? lpf + dx : lpf) * 3 + c) * gf.plane;
+            // y-z weighted sum of local fine plane lpf (global Gf) around (2J, 2K); 0 for a plane outside the grid / the slab
+            auto yz_sum = [&](int Gf, int lpf) -> double {
+                const bool xok = !(Gf < 0 || Gf > gf.nx || lpf < 0 || lpf >= gf.NPX);
+                const double* __restrict__ fplane = resf + (long long)((xok ? lpf : 0) * 3 + c) * gf.plane;
+                double acc = 0.0;
 #pragma unroll
                 for (int dy = -1; dy <= 1; ++dy) {
                     const int jf = 2 * J + dy;
@@ -95,11 +99,22 @@ __global__ void __launch_bounds__(256) k_restrict(GridDev gf, GridDev gc, int cp
                     if (ok) v = *reinterpret_cast<const double2*>(row + kf);
                     double left = __shfl_up_sync(0xffffffffu, v.y, 1);
                     if (!left_in_lane) left = (ok && K > 0) ? row[kf - 1] : 0.0;
-                    const double w = (dx ? 0.5 : 1.0) * (dy ? 0.5 : 1.0);
-                    acc = fma(w, v.x + 0.5 * (v.y + left), acc);
+                    acc = fma(dy ? 0.5 : 1.0, v.x + 0.5 * (v.y + left), acc);
+                }
+                return acc;
+            };
+            const int Gf0 = 2 * (gc.gp0 + L0), lpf0 = Gf0 - gf.gp0;
+            double carry = yz_sum(Gf0 - 1, lpf0 - 1);
+            for (int Lp = L0; Lp < L1; ++Lp) {
+                const int Gf = 2 * (gc.gp0 + Lp), lpf = Gf - gf.gp0;
+                const double mid = yz_sum(Gf, lpf), hi = yz_sum(Gf + 1, lpf + 1);
+                const double acc = fma(0.5, carry, fma(0.5, hi, mid));
+                carry = hi;
+                if (node) {
+                    const uint8_t m = maskc[(long long)Lp * gc.plane + id];
+                    rc[(long long)(Lp * 3 + c) * gc.plane + id] = ((m >> c) & 1) ? 0.0 : acc;
                 }
             }
-            if (node) out[id] = ((mrow[id] >> c) & 1) ? 0.0 : acc;
         }
     }
 }
@@ -569,8 +584,9 @@ static int mg_vcycle(esimp_ctx* ctx, int l, bool first_done = false, int dot_slo
         {
             const int cp0 = (fp0g + 1) / 2, cp1 = (fp1g - 1) / 2 + 1;
             const int nJK = (C.vw.g.ny + 1) * C.vw.g.nzp;
-            dim3 grid((unsigned)std::min(64, (nJK + 255) / 256), (unsigned)std::max(1, std::min(65535, (cp1 - cp0) * 3)));
-            k_restrict<<<grid, 256, 0, ctx->stream>>>(L.vw.g, C.vw.g, cp0, cp1, L.d_q, C.d_mask, C.d_r);
+            const int chunk = restrict_chunk((long long)nJK * 3 * (cp1 - cp0));
+            dim3 grid((unsigned)std::min(64, (nJK + 255) / 256), (unsigned)std::max(1, std::min(65535, (cp1 - cp0 + chunk - 1) / chunk * 3)));
+            k_restrict<<<grid, 256, 0, ctx->stream>>>(L.vw.g, C.vw.g, cp0, cp1, chunk, L.d_q, C.d_mask, C.d_r);
             ctx->launches++;
             ESIMP_CUDA(cudaGetLastError());
         }
@@ -581,8 +597,10 @@ static int mg_vcycle(esimp_ctx* ctx, int l, bool first_done = false, int dot_slo
         {
             PROF_BEGIN(ctx, PROF_RESTRICT, l == 0)
             const int nJK = (C.vw.g.ny + 1) * C.vw.g.nzp;
-            dim3 grid((unsigned)std::min(64, (nJK + 255) / 256), (unsigned)std::max(1, std::min(65535, (C.vw.own_p1 - C.vw.own_p0) * 3)));
-            k_restrict<<<grid, 256, 0, ctx->stream>>>(L.vw.g, C.vw.g, C.vw.own_p0, C.vw.own_p1, L.d_q, C.d_mask, C.d_r);
+            const int chunk = restrict_chunk((long long)nJK * 3 * (C.vw.own_p1 - C.vw.own_p0));
+            dim3 grid((unsigned)std::min(64, (nJK + 255) / 256),
+                      (unsigned)std::max(1, std::min(65535, (C.vw.own_p1 - C.vw.own_p0 + chunk - 1) / chunk * 3)));
+            k_restrict<<<grid, 256, 0, ctx->stream>>>(L.vw.g, C.vw.g, C.vw.own_p0, C.vw.own_p1, chunk, L.d_q, C.d_mask, C.d_r);
             ctx->launches++;
             ESIMP_CUDA(cudaGetLastError());
             PROF_END(ctx)
@@ -649,6 +667,7 @@ int pcg_solve_mg(esimp_ctx* ctx, int* iters, double* relres) {
     const double tol2 = ctx->prm.pcg_rtol * ctx->prm.pcg_rtol * ff;
     double rr = ctx->h_scal[SC_RR0];
     int it = 0, status = ESIMP_OK;
+    const bool lag = ctx->mg_lag < 0 ? ctx->nranks > 1 : ctx->mg_lag > 0;  // auto: multi-rank only (measured at N = 1: +2 % per SIMP step)
     if (ff == 0.0) {
         ESIMP_CUDA(cudaMemsetAsync(ctx->d_u, 0, sizeof(double) * ctx->ndof_loc, ctx->stream));
         rr = 0.0;
@@ -683,19 +702,42 @@ int pcg_solve_mg(esimp_ctx* ctx, int* iters, double* relres) {
             ESIMP_TRY(allreduce_scalars(ctx, SC_RR0, 1, false));
         }
         ++it;
-        {
-            const auto w0 = std::chrono::steady_clock::now();
-            ESIMP_TRY(fetch_scalars(ctx));
-            clock.wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
-            clock.fetches++;
-        }
-        rr = ctx->h_scal[SC_RR0];
-        if (getenv("ESIMP_MG_DEBUG") && ctx->rank == 0)
-            fprintf(stderr, "[mg] it %d rr %.6e pq %.6e rz %.6e\n", it, rr, ctx->h_scal[SC_PQ], ctx->h_scal[RZ[cur]]);
-        if (!(rr == rr)) return esimp_fail(ctx, ESIMP_ERR_STATE, "PCG breakdown: residual is NaN");
-        if (rr <= tol2 || it >= ctx->prm.pcg_maxit) {  // only the deferred x += alpha p is left to do
-            LAUNCH_STREAM(k_mg_direction, L0.d_z, ctx->d_p, ctx->d_u, i0, i1, S + RZ[cur], S + RZ[cur], S + SC_PQ, 2);
-            break;
+        if (lag && it < ctx->prm.pcg_maxit) {
+            // lagged poll: leave <r,r> of this iteration in the pinned ring and look at the previous iteration's instead
+            double* ring = ctx->h_scal + N_SCAL;
+            ESIMP_CUDA(cudaMemcpyAsync(ring + (it & 1), S + SC_RR0, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            ESIMP_CUDA(cudaEventRecord(ctx->lag_ev[it & 1], ctx->stream));
+            if (it >= 2) {
+                const auto w0 = std::chrono::steady_clock::now();
+                ESIMP_CUDA(cudaEventSynchronize(ctx->lag_ev[(it - 1) & 1]));
+                clock.wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+                clock.fetches++;
+                const double rr_prev = ring[(it - 1) & 1];
+                if (!(rr_prev == rr_prev)) return esimp_fail(ctx, ESIMP_ERR_STATE, "PCG breakdown: residual is NaN");
+                if (rr_prev <= tol2) {
+                    // iteration it - 1 had converged: the direction kernel of that pass has already applied x += alpha_{it-1} p, and
+                    // the update of this surplus iteration is deferred and never applied, so x is the iterate of iteration it - 1
+                    rr = rr_prev;
+                    --it;
+                    break;
+                }
+                rr = rr_prev;  // not converged: rr only has to stay above tol2 for the loop condition
+            }
+        } else {
+            {
+                const auto w0 = std::chrono::steady_clock::now();
+                ESIMP_TRY(fetch_scalars(ctx));
+                clock.wait_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - w0).count();
+                clock.fetches++;
+            }
+            rr = ctx->h_scal[SC_RR0];
+            if (getenv("ESIMP_MG_DEBUG") && ctx->rank == 0)
+                fprintf(stderr, "[mg] it %d rr %.6e pq %.6e rz %.6e\n", it, rr, ctx->h_scal[SC_PQ], ctx->h_scal[RZ[cur]]);
+            if (!(rr == rr)) return esimp_fail(ctx, ESIMP_ERR_STATE, "PCG breakdown: residual is NaN");
+            if (rr <= tol2 || it >= ctx->prm.pcg_maxit) {  // only the deferred x += alpha p is left to do
+                LAUNCH_STREAM(k_mg_direction, L0.d_z, ctx->d_p, ctx->d_u, i0, i1, S + RZ[cur], S + RZ[cur], S + SC_PQ, 2);
+                break;
+            }
         }
         bool dot_done = false;
         ESIMP_TRY(mg_vcycle(ctx, 0, true, RZ[nxt], &dot_done));  // <r,z> comes out of the last fused smoother step

@@ -115,6 +115,12 @@ struct SweepSmem {
 // the carry rows follow the struct: carry[ci][row][3] = z-high face sums of lane 31 (per node row, component), read by
 // lane 0 one segment later; row ci = 0 .. nsteps (output planes of the chunk)
 constexpr int SW_CARRY_ROW = SW_CROWS * 3;
+// Store-phase operands read from shared memory BEFORE the y stage instead of next to their use (the consumer warps issue in order and
+// nothing independent is left at the tail of a step, so a load placed there exposes its whole latency): bit 0 = u for <u, y>
+// (FUSE_DOT), bit 1 = r / Dinv / z / z_prev of the lower node row (smoother modes), bit 2 = of the middle row as well
+#ifndef SW_PRELOAD
+#define SW_PRELOAD 0
+#endif
 
 template <int MODE>
 struct SweepTraits {
@@ -334,6 +340,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
                     // a plane outside [P0, P1) (the first one of a chunk that starts with the redundant layer) goes through the same
                     // exchange so that the slot / parity bookkeeping stays in step with the input ring; only its stores are skipped
                     const bool plane_ok = lp >= P0 && lp < P1;  // CTA-uniform
+                    constexpr bool PRE_DOT = MODE == FUSE_DOT && (SW_PRELOAD & 1) != 0;
+                    constexpr bool PRE_SM = TR::SMOOTH && (SW_PRELOAD & 6) != 0;
+                    constexpr int PRE_NROWS = PRE_DOT ? 2 : (PRE_SM ? ((SW_PRELOAD & 4) ? 2 : 1) : 0);  // node rows r < PRE_NROWS are preloaded
+                    double pu[2][3], pr[2][3], pdi[2][3], pz2[2][3];
                     const bool last_seg = s == nseg - 1;
                     const bool ext = extra && last_seg && lane == 31;
                     const bool col_ok = plane_ok && 32 * s + lane <= g.nz;
@@ -350,12 +360,13 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
                         // operands of this node: my own column from the {32, 15, 3} box, the extra column from the {2, 15, 3} one
                         const double* op = col ? fzxp + c * SW_OROWS * 2 + r * 2 : fzp + c * SW_OROWS * 32 + r * 32;
                         const int ostride = col ? SW_OPX_SLOT : SW_OP_BOX;
+                        const bool pre = col == 0 && r < PRE_NROWS;  // operands of this node were read before the y stage
                         if (TR::SMOOTH) {
-                            const double rv = op[0];
-                            const double dinv = op[(1 % NFS) * ostride];
-                            const double zin = uin[c * SW_ROWS * SW_BOXZ + r * SW_BOXZ + col];
-                            const double dprev = a.dmode == FUSE_D_BUFFER ? op[(2 % NFS) * ostride]
-                                               : a.dmode == FUSE_D_FROM_ZPREV ? zin - op[(2 % NFS) * ostride] : zin;  // FUSE_D_IS_Z / unused
+                            const double rv = pre && PRE_SM ? pr[r][c] : op[0];
+                            const double dinv = pre && PRE_SM ? pdi[r][c] : op[(1 % NFS) * ostride];
+                            const double zin = pre && PRE_SM ? pu[r][c] : uin[c * SW_ROWS * SW_BOXZ + r * SW_BOXZ + col];
+                            const double third = pre && PRE_SM ? pz2[r][c] : op[(2 % NFS) * ostride];
+                            const double dprev = a.dmode == FUSE_D_BUFFER ? third : a.dmode == FUSE_D_FROM_ZPREV ? zin - third : zin;  // FUSE_D_IS_Z / unused
                             const double v = fma(a.c1, dprev, a.c2 * dinv * (rv - s_val));
                             if (a.write_d) dp[off] = v;
                             const double znew = zin + v;
@@ -365,7 +376,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
                             yp[off] = op[0] - s_val;
                         } else {
                             yp[off] = s_val;
-                            if (MODE == FUSE_DOT) pq[0] = fma(s_val, uin[c * SW_ROWS * SW_BOXZ + r * SW_BOXZ + col], pq[0]);
+                            if (MODE == FUSE_DOT) pq[0] = fma(s_val, pre && PRE_DOT ? pu[r][c] : uin[c * SW_ROWS * SW_BOXZ + r * SW_BOXZ + col], pq[0]);
                         }
                     };
                     // z stage of one node row: m[c][0 / 1] = z-even / z-odd coefficient (complete over y)
@@ -395,6 +406,20 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
                         }
                     };
                     if (NF > 0 && plane_ok) sw_bar_wait_a(sw_bar_at(b_ffull, fs), fpar);
+                    if (PRE_DOT || PRE_SM) {
+#pragma unroll
+                        for (int r = 0; r < PRE_NROWS; ++r)
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) {
+                                pu[r][c] = uin[c * SW_ROWS * SW_BOXZ + r * SW_BOXZ];
+                                if (PRE_SM) {
+                                    const double* op = fzp + c * SW_OROWS * 32 + r * 32;
+                                    pr[r][c] = op[0];
+                                    pdi[r][c] = op[(1 % NFS) * SW_OP_BOX];
+                                    pz2[r][c] = op[(2 % NFS) * SW_OP_BOX];
+                                }
+                            }
+                    }
                     // ---- y stage inside the thread: the middle node row is complete, the upper one goes to the warp above
                     double m1[3][2];
 #pragma unroll

@@ -295,6 +295,40 @@ def test_gmg_solve_matches_direct(gpu_ctx_factory, nel, right, variant):
     assert iters[1] * 5 < iters[0], iters
 
 
+def test_gmg_lagged_poll_returns_the_same_iterate(gpu_ctx_factory, monkeypatch):
+    """The lagged convergence poll of the multigrid-preconditioned CG (the host enqueues iteration k before it looks at <r,r> of
+    iteration k-1, csrc/multigrid.cu) stops at the same iteration with bit-identical displacements as the blocking poll."""
+    nel, right = (32, 16, 16), (32.0, 16.0, 16.0)
+    g = o.generate_grid_hex(nel, (0, 0, 0), right)
+    dofs = o.distribute_dofs(g)
+    rng = np.random.default_rng(5)
+    rho = 1e-3 + (1 - 1e-3) * rng.random(g.n_cells)
+    pres = np.sort(dofs[np.array(sorted(o.select_nodes_by_plane(g, [0, 0, 0], [1, 0, 0], 1e-6)))].ravel())
+    f = o.apply_point_load(np.zeros(3 * g.n_nodes), dofs, sorted(o.select_nodes_by_plane(g, [right[0], 0, 0], [1, 0, 0], 1e-6)), [0.0, -1.0, 0.5])
+    res = {}
+    for lag in ("0", "1"):
+        monkeypatch.setenv("ESIMP_PCG_LAG", lag)
+        for rtol in (1e-4, 1e-10):
+            ctx = make_ctx(gpu_ctx_factory, g, dofs, pres, pcg_rtol=rtol, precond=1)
+            ctx.set_load(f)
+            ctx.set_density(rho)
+            u, it, relres, st = ctx.solve()
+            assert st == 0 and relres <= rtol
+            res[lag, rtol] = (u, it, relres)
+            ctx.close()
+    for rtol in (1e-4, 1e-10):
+        assert res["0", rtol][1] == res["1", rtol][1] and res["0", rtol][2] == res["1", rtol][2]
+        assert np.array_equal(res["0", rtol][0], res["1", rtol][0])
+    # maxit reached inside the lagged loop: blocking fall-back on the last iteration, warning status
+    monkeypatch.setenv("ESIMP_PCG_LAG", "1")
+    ctx = make_ctx(gpu_ctx_factory, g, dofs, pres, pcg_rtol=1e-14, pcg_maxit=5, precond=1)
+    ctx.set_load(f)
+    ctx.set_density(rho)
+    _, it, _, st = ctx.solve()
+    assert it == 5 and st != 0
+    ctx.close()
+
+
 def test_loop_c1_cantilever_golden_gmg(gpu_ctx_factory, golden_dir):
     """BASELINE config 1 with the multigrid-preconditioned solve: same golden bars (compliance 1e-6, density 1e-3)."""
     gz = np.load(golden_dir / "c1_cantilever_60x20x4.npz")
