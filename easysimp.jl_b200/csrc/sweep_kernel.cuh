@@ -117,9 +117,12 @@ struct SweepSmem {
 constexpr int SW_CARRY_ROW = SW_CROWS * 3;
 // Store-phase operands read from shared memory BEFORE the y stage instead of next to their use (the consumer warps issue in order and
 // nothing independent is left at the tail of a step, so a load placed there exposes its whole latency): bit 0 = u for <u, y>
-// (FUSE_DOT), bit 1 = r / Dinv / z / z_prev of the lower node row (smoother modes), bit 2 = of the middle row as well
+// (FUSE_DOT), bit 1 = r / Dinv / z / z_prev of the lower node row (smoother modes), bit 2 = of the middle row as well.
+// Measured inside the SIMP step at 512x256x256 (r2 call 23): 0 -> 3.068 it/s, 1 -> 3.075 (dot launch 0.628 -> 0.612 ms), 3 -> 3.110
+// (smoother launch 0.838 -> 0.815 ms), 7 -> 2.852 (register spills).  Also tried and dropped: <u, y> gathered cell by cell in mode space
+// (no second read of u, but 12 more live doubles: spills, 0.88 ms) and one accumulator per component (no change)
 #ifndef SW_PRELOAD
-#define SW_PRELOAD 0
+#define SW_PRELOAD 3
 #endif
 
 template <int MODE>
