@@ -123,6 +123,8 @@ int esimp_create(esimp_ctx** out, int device) {
     if (const char* e = getenv("ESIMP_MG_REPLICATE")) ctx->mg_replicate = atoi(e);
     if (const char* e = getenv("ESIMP_MG_REPLICATE_CELLS")) ctx->mg_replicate_cells = atoll(e);
     if (const char* e = getenv("ESIMP_PCG_LAG")) ctx->mg_lag = atoi(e);
+    if (const char* e = getenv("ESIMP_MG_TAIL")) ctx->mg_tail = atoi(e);
+    if (const char* e = getenv("ESIMP_MG_TAIL_NODES")) ctx->mg_tail_nodes = atoll(e);
     auto bail = [&](const char* what) {
         std::string msg = std::string(what) + ": " + cudaGetErrorString(cudaGetLastError());
         esimp_destroy(ctx);  // frees whatever was created so far
@@ -154,6 +156,7 @@ int esimp_destroy(esimp_ctx* ctx) {
     cudaFree(ctx->d_partial_mv);
     cudaFree(ctx->d_ticket);
     cudaFree(ctx->d_scal);
+    cudaFree(ctx->d_K0);
     cudaFreeHost(ctx->h_scal);
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -260,6 +263,7 @@ int esimp_set_grid_structured(esimp_ctx* ctx, int nx, int ny, int nz, double hx,
         ESIMP_CUDA(cudaMemcpy(ctx->d_dof_of_node, dof_of_node, sizeof(int64_t) * ctx->n_dofs_global, cudaMemcpyHostToDevice));
         // keep a host inverse for esimp_set_dirichlet
     }
+    if (ctx->nranks > 1) ESIMP_TRY(comm_p2p_setup(ctx, 3 * g.plane));  // collective: node-plane halos over peer memory when IPC works
     return ESIMP_OK;
 }
 

@@ -93,6 +93,16 @@ struct esimp_ctx {
     // ---- distributed
     int rank = 0, nranks = 1;
     void* nccl_comm = nullptr;
+    // peer-memory halo exchange of node planes (comm.cu): every rank owns one mailbox (2 sides x 2 parities x one fine node plane)
+    // and one flag block, both mapped into the x-neighbours through CUDA IPC; a single kernel pushes the boundary planes over NVLink,
+    // signals, waits for the neighbours' signal and unpacks.  p2p = 0: not set up (NCCL send / recv), 1: active, -1: unavailable
+    int p2p = 0;
+    double* p2p_mail = nullptr;               // [side from: 0 left, 1 right][parity][p2p_plane_cap]
+    unsigned long long* p2p_flags = nullptr;  // [0] epoch written by the left neighbour, [1] by the right one, [2] CTA ticket, [3] timeouts
+    double* p2p_peer_mail[2] = {nullptr, nullptr};               // the left / right neighbour's mailbox (IPC mappings)
+    unsigned long long* p2p_peer_flags[2] = {nullptr, nullptr};  // ... and flag block
+    long long p2p_plane_cap = 0;                                  // doubles per mailbox slot
+    unsigned long long p2p_epoch[2] = {0, 0};                     // exchanges done with the left / right neighbour
 
     // ---- mesh kind
     bool structured = false, unstructured = false;
@@ -118,12 +128,15 @@ struct esimp_ctx {
     int mg_min_layers = 1;  // multi-rank: stop coarsening when a rank would hold fewer cell layers than this
     int mg_nu = 2, mg_coarse_its = 16;  // tuned on 512x256x256 (scripts/mg_sweep.sh): nu 2, ratio 10 is the fastest
     double mg_ratio = 10.0;
-    // GMG-CG convergence poll: 0 = read <r,r> back after every iteration (the host waits for the device once per iteration),
-    // 1 = lagged: iteration k is enqueued before <r,r> of iteration k-1 is looked at, so the host runs one iteration ahead and the
-    // tiny coarse-level launches / NCCL calls never starve the device.  The iterate returned is the same (the deferred x update of
-    // the surplus iteration is never applied).  -1 = auto: lagged on multi-rank contexts only (on one B200 the fine-grid kernels are long enough for the host to keep ahead and
-    // the lagged poll measured 2 % slower); ESIMP_PCG_LAG = 0 / 1 forces it
+    // GMG-CG convergence poll: 0 / -1 = read <r,r> back after every iteration (the host waits for the device once per iteration),
+    // 1 = lagged: iteration k is enqueued before <r,r> of iteration k-1 is looked at, so the host runs one iteration ahead.  The
+    // iterate returned is the same (the deferred x update of the surplus iteration is never applied).  Opt-in (ESIMP_PCG_LAG=1):
+    // on 1 and 2 B200s the fine-grid kernels are long enough for the host to keep ahead and the lagged poll measured 2 % slower
     int mg_lag = -1;
+    // levels >= mg_tail_start run inside ONE cluster kernel (coarse_tail.cuh); 0 = none.  ESIMP_MG_TAIL=0 switches the tail off
+    int mg_tail = 1, mg_tail_start = 0;
+    long long mg_tail_nodes = 10000;  // largest level (nodes) the tail takes (ESIMP_MG_TAIL_NODES)
+    double* d_K0 = nullptr;  // dense 24 x 24 unit element matrix for the tail kernel
     cudaEvent_t lag_ev[2]{};
 
     // element matrices (host copies; uploaded to __constant__ on demand)
@@ -277,6 +290,7 @@ void tet4_element_matrix(const double* xyz4, double lam, double mu, double* ke12
 // comm.cu
 int comm_unique_id(void* id128, std::string& err);
 int comm_init(esimp_ctx* ctx, int rank, int nranks, const void* id128);
+int comm_p2p_setup(esimp_ctx* ctx, long long plane_doubles);  // after the slab is known; falls back to NCCL when IPC is unavailable
 void comm_destroy(esimp_ctx* ctx);
 int comm_allreduce(esimp_ctx* ctx, double* d_buf, long long n, bool is_max);
 int comm_allreduce_f32(esimp_ctx* ctx, float* d_buf, long long n);

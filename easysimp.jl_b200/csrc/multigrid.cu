@@ -30,6 +30,7 @@
 #include <chrono>
 
 #include "ctx.cuh"
+#include "coarse_tail.cuh"
 
 #define LAUNCH_STREAM(kern, ...)                                        \
     do {                                                                \
@@ -465,11 +466,13 @@ static int mg_estimate_lmax(esimp_ctx* ctx, MGLevel& L, int iters) {
     return ESIMP_OK;
 }
 
+static void mg_plan_tail(esimp_ctx* ctx);
 int mg_setup(esimp_ctx* ctx) {
     if (!ctx->structured) return esimp_fail(ctx, ESIMP_ERR_STATE, "the multigrid preconditioner needs a structured grid");
     if (ctx->mg.empty() || ctx->mg_bc_version != ctx->bc_version) {
         ESIMP_TRY(mg_build_levels(ctx));
         ctx->mg_bc_version = ctx->bc_version;
+        mg_plan_tail(ctx);
     }
     ctx->mg[0].diag_value = ctx->diag_value;
     for (size_t l = 1; l < ctx->mg.size(); ++l) {
@@ -554,9 +557,75 @@ static int mg_smooth(esimp_ctx* ctx, MGLevel& L, int k, bool zero_guess, bool fi
     return ESIMP_OK;
 }
 
+
+// which levels the single-kernel tail of the V-cycle takes: the longest run of trailing levels that are whole on this rank, small
+// enough for one cluster and at most CT_MAX_LEVELS long; never the fine grid
+static void mg_plan_tail(esimp_ctx* ctx) {
+    ctx->mg_tail_start = 0;
+    if (!ctx->mg_tail) return;
+    const int n = (int)ctx->mg.size();
+    int t = n;
+    while (t - 1 >= 1 && n - (t - 1) <= CT_MAX_LEVELS) {
+        const MGLevel& L = ctx->mg[t - 1];
+        const GridDev& g = L.vw.g;
+        const bool whole = (ctx->nranks == 1 || L.replicated) && g.gp0 == 0 && g.ge0 == 0 && g.e2p == 0 && g.NPX == g.nx + 1 && g.NEX == g.nx;
+        if (!whole || (long long)(g.nx + 1) * (g.ny + 1) * (g.nz + 1) > std::min(CT_MAX_NODES, ctx->mg_tail_nodes)) break;
+        if (coarse_tail_slab_doubles(g.nx, g.ny, g.nz) * 8 > 200 * 1024) break;
+        --t;
+    }
+    if (t < n) ctx->mg_tail_start = t;
+}
+// z_l = V(r_l) for l = mg_tail_start, all levels below included, in one launch
+static int mg_tail_cycle(esimp_ctx* ctx) {
+    const int t = ctx->mg_tail_start, n = (int)ctx->mg.size();
+    if (!ctx->d_K0) {
+        ESIMP_CUDA(cudaMalloc(&ctx->d_K0, sizeof(double) * 576));
+        ESIMP_CUDA(cudaMemcpyAsync(ctx->d_K0, ctx->K0, sizeof(double) * 576, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CoarseTailArgs a{};
+    a.nlev = n - t;
+    a.nu = ctx->mg_nu;
+    a.coarse_its = ctx->mg_coarse_its;
+    a.K0 = ctx->d_K0;
+    for (int l = t; l < n; ++l) {
+        MGLevel& L = ctx->mg[l];
+        CoarseTailLevel& T = a.lv[l - t];
+        T.nx = L.vw.g.nx;
+        T.ny = L.vw.g.ny;
+        T.nz = L.vw.g.nz;
+        T.nzp = L.vw.g.nzp;
+        T.E = L.d_E;
+        T.mask = L.d_mask;
+        T.dinv = L.d_dinv;
+        T.r = L.d_r;
+        T.za = L.d_z;
+        T.zb = L.d_z2;
+        T.q = L.d_q;
+        const double lmax = L.lmax, lmin = lmax / ctx->mg_ratio;
+        T.theta = 0.5 * (lmax + lmin);
+        T.delta = 0.5 * (lmax - lmin);
+    }
+    long long sdbl = 0;
+    for (int l = t; l < n; ++l) sdbl = std::max(sdbl, coarse_tail_slab_doubles(ctx->mg[l].vw.g.nx, ctx->mg[l].vw.g.ny, ctx->mg[l].vw.g.nz));
+    static unsigned long long attr_devices = 0;
+    const unsigned long long dev_bit = 1ull << (ctx->device & 63);
+    if (!(attr_devices & dev_bit)) {
+        ESIMP_CUDA(cudaFuncSetAttribute(k_coarse_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_devices |= dev_bit;
+    }
+    k_coarse_tail<<<CT_CTAS, CT_THREADS, (size_t)sdbl * 8, ctx->stream>>>(a);
+    ctx->launches++;
+    ESIMP_CUDA(cudaGetLastError());
+    // where the kernel left z of its first level: one buffer swap per smoother step that applies the operator
+    const int swaps = a.nlev == 1 ? ctx->mg_coarse_its - 1 : (ctx->mg_nu - 1) + ctx->mg_nu;
+    if (swaps & 1) std::swap(ctx->mg[t].d_z, ctx->mg[t].d_z2);
+    return ESIMP_OK;
+}
+
 // z_l = V(r_l).  Level 0 only: first_done / dot_slot / dot_done as in mg_smooth.
 static int mg_vcycle(esimp_ctx* ctx, int l, bool first_done = false, int dot_slot = -1, bool* dot_done = nullptr) {
     MGLevel& L = ctx->mg[l];
+    if (l > 0 && l == ctx->mg_tail_start) return mg_tail_cycle(ctx);
     if (l == (int)ctx->mg.size() - 1)
         return mg_smooth(ctx, L, l == 0 ? ctx->mg_nu : ctx->mg_coarse_its, true, first_done, dot_slot, dot_done);
     MGLevel& C = ctx->mg[l + 1];
@@ -667,7 +736,7 @@ int pcg_solve_mg(esimp_ctx* ctx, int* iters, double* relres) {
     const double tol2 = ctx->prm.pcg_rtol * ctx->prm.pcg_rtol * ff;
     double rr = ctx->h_scal[SC_RR0];
     int it = 0, status = ESIMP_OK;
-    const bool lag = ctx->mg_lag < 0 ? ctx->nranks > 1 : ctx->mg_lag > 0;  // auto: multi-rank only (measured at N = 1: +2 % per SIMP step)
+    const bool lag = ctx->mg_lag > 0;  // opt-in (ESIMP_PCG_LAG=1): measured +2 % per SIMP step at N = 1, +1.7 % at N = 2
     if (ff == 0.0) {
         ESIMP_CUDA(cudaMemsetAsync(ctx->d_u, 0, sizeof(double) * ctx->ndof_loc, ctx->stream));
         rr = 0.0;

@@ -329,6 +329,30 @@ def test_gmg_lagged_poll_returns_the_same_iterate(gpu_ctx_factory, monkeypatch):
     ctx.close()
 
 
+@pytest.mark.parametrize("nel,right", [((64, 32, 32), (64.0, 32.0, 32.0)), ((48, 24, 12), (4.0, 2.0, 1.0))])
+def test_gmg_cluster_tail_equals_level_by_level_cycle(gpu_ctx_factory, monkeypatch, nel, right):
+    """The bottom levels of the V-cycle run as one thread-block-cluster kernel (csrc/coarse_tail.cuh).  It is the same preconditioner
+    as the level-by-level path up to summation order: same CG iteration count (+-1) and the same displacement."""
+    g = o.generate_grid_hex(nel, (0, 0, 0), right)
+    dofs = o.distribute_dofs(g)
+    rng = np.random.default_rng(6)
+    rho = 1e-3 + (1 - 1e-3) * rng.random(g.n_cells) ** 3
+    pres = np.sort(dofs[np.array(sorted(o.select_nodes_by_plane(g, [0, 0, 0], [1, 0, 0], 1e-6)))].ravel())
+    f = o.apply_point_load(np.zeros(3 * g.n_nodes), dofs, sorted(o.select_nodes_by_plane(g, [right[0], 0, 0], [1, 0, 0], 1e-6)), [0.0, -1.0, 0.5])
+    res = {}
+    for tail in ("0", "1"):
+        monkeypatch.setenv("ESIMP_MG_TAIL", tail)
+        ctx = make_ctx(gpu_ctx_factory, g, dofs, pres, pcg_rtol=1e-10, precond=1)
+        ctx.set_load(f)
+        ctx.set_density(rho)
+        u, it, relres, st = ctx.solve()
+        assert st == 0 and relres <= 1e-10
+        res[tail] = (u, it)
+        ctx.close()
+    assert abs(res["0"][1] - res["1"][1]) <= 1, (res["0"][1], res["1"][1])
+    assert relmax(res["0"][0], res["1"][0]) < 1e-7
+
+
 def test_loop_c1_cantilever_golden_gmg(gpu_ctx_factory, golden_dir):
     """BASELINE config 1 with the multigrid-preconditioned solve: same golden bars (compliance 1e-6, density 1e-3)."""
     gz = np.load(golden_dir / "c1_cantilever_60x20x4.npz")
