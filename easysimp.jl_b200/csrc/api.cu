@@ -814,7 +814,7 @@ int esimp_profile_enable(esimp_ctx* ctx, int on) {
         for (auto& e : ctx->prof_ev) ESIMP_CUDA(cudaEventCreate(&e));
         for (auto& e : ctx->prof_coarse_ev) ESIMP_CUDA(cudaEventCreate(&e));
     }
-    ctx->prof_on = on != 0;
+    ctx->prof_on = on < 0 ? 0 : (on > 2 ? 2 : on);
     for (int c = 0; c < PROF_NCAT; ++c) {
         ctx->prof_ms_cat[c] = 0.0;
         ctx->prof_cnt_cat[c] = 0;

@@ -219,9 +219,11 @@ __global__ void __launch_bounds__(P2P_THREADS) k_halo_p2p(double* v, long long n
 // Allocate the mailbox + flags, exchange their IPC handles through the NCCL communicator and map the neighbours'.  Collective.
 int comm_p2p_setup(esimp_ctx* ctx, long long plane_doubles) {
     if (ctx->nranks <= 1 || ctx->p2p != 0) return ESIMP_OK;
-    // opt-in: on 2 B200s an exchange costs 24.0 us with 96 CTAs (26.9 us with 32) against 25.9 us for the NCCL group -- what both pay is
-    // the launch and the wait for the neighbour, not the 1.6 MB transfer (profiles/r2_bench_c5_n2_p2p_halo.log)
-    static const int enabled = getenv("ESIMP_P2P_HALO") ? atoi(getenv("ESIMP_P2P_HALO")) : 0;
+    // default: on from 4 ranks.  On 2 B200s an exchange costs 24.0 us with 96 CTAs (26.9 us with 32) against 25.9 us for the NCCL group
+    // (what both pay is the launch and the wait for the neighbour, not the 1.6 MB transfer); on 8 B200s 23.9 us against 31.8 us, the
+    // SIMP step 108.8 ms against 113.3 ms with bit-identical compliance histories (profiles/r2_bench_c5_n8_*.json).
+    // ESIMP_P2P_HALO = 0 / 1 forces NCCL / peer memory
+    const int enabled = getenv("ESIMP_P2P_HALO") ? atoi(getenv("ESIMP_P2P_HALO")) : (ctx->nranks >= 4 ? 1 : 0);
     ctx->p2p = -1;
     if (!enabled) return ESIMP_OK;
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;

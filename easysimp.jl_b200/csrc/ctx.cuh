@@ -81,6 +81,12 @@ struct UnstructuredMesh {
     double* d_xcell = nullptr;       // [3*npe][n_cells] node coordinates of each cell
 };
 
+// __constant__ blocks have one copy per DEVICE; who uploaded one last is tracked per device under this lock, so that contexts on
+// different GPUs of one process (one host thread each) do not invalidate or race each other's uploads.  Two contexts on the SAME
+// device with different cuboids still share the block: drive them one after the other (every entry point drains its stream).
+#include <mutex>
+inline std::mutex g_const_mutex;
+
 struct NcclApi;  // comm.cu
 
 struct esimp_ctx {
@@ -177,7 +183,7 @@ struct esimp_ctx {
     double f_norm2 = 0.0;
     cudaEvent_t ev[6]{};
     // in-region timing of the operator kernel (esimp_profile_*): event pairs recorded on ctx->stream
-    bool prof_on = false;
+    int prof_on = 0;  // 0 off, 1 = event pairs around the plain / dot operator launches only (cheap enough for a timed region), 2 = every category
     std::vector<cudaEvent_t> prof_ev;
     std::vector<uint8_t> prof_tag;
     int prof_n = 0;
@@ -196,7 +202,7 @@ enum { PROF_OP_PLAIN = 0, PROF_OP_SMOOTH = 1, PROF_OP_RESID = 2, PROF_FILTER = 3
        PROF_COMM_HALO = 11, PROF_COMM_ALLREDUCE = 12, PROF_COMM_LEVELSUM = 13, PROF_MG_COARSE = 14, PROF_HOST_PCG = 15, PROF_HOST_WAIT = 16, PROF_NCAT = 17 };
 // bracket the launches between PROF_BEGIN and PROF_END with an event pair on the context's stream while profiling is on
 #define PROF_BEGIN(ctx, cat, cond)                                                                         \
-    const bool _prof_timed = (ctx)->prof_on && (cond) && 2 * (ctx)->prof_n + 1 < (int)(ctx)->prof_ev.size(); \
+    const bool _prof_timed = (ctx)->prof_on >= ((cat) == PROF_OP_PLAIN ? 1 : 2) && (cond) && 2 * (ctx)->prof_n + 1 < (int)(ctx)->prof_ev.size(); \
     if (_prof_timed) {                                                                                     \
         (ctx)->prof_tag[(ctx)->prof_n] = (cat);                                                            \
         cudaEventRecord((ctx)->prof_ev[2 * (ctx)->prof_n], (ctx)->stream);                                 \

@@ -19,7 +19,7 @@
 constexpr int MAX_STENCIL = 1100;
 __constant__ int c_st_di[MAX_STENCIL], c_st_dj[MAX_STENCIL], c_st_dk[MAX_STENCIL];
 __constant__ double c_st_w[MAX_STENCIL];
-static const esimp_ctx* g_stencil_owner = nullptr;
+static const esimp_ctx* g_stencil_owner[64] = {};  // per device
 
 #define LAUNCH_STREAM(kern, ...)                                        \
     do {                                                                \
@@ -43,10 +43,12 @@ int simp_modulus(esimp_ctx* ctx) {
 
 // ---------------------------------------------------------------------------- stencil filter
 void filter_forget_ctx(const esimp_ctx* ctx) {
-    if (g_stencil_owner == ctx) g_stencil_owner = nullptr;
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    if (g_stencil_owner[ctx->device & 63] == ctx) g_stencil_owner[ctx->device & 63] = nullptr;
 }
 static int upload_stencil(esimp_ctx* ctx) {
-    if (g_stencil_owner == ctx) return ESIMP_OK;
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    if (g_stencil_owner[ctx->device & 63] == ctx) return ESIMP_OK;
     std::vector<int> di(ctx->st_n), dj(ctx->st_n), dk(ctx->st_n);
     for (int s = 0; s < ctx->st_n; ++s) {
         di[s] = ctx->st_off[3 * s];
@@ -57,7 +59,7 @@ static int upload_stencil(esimp_ctx* ctx) {
     ESIMP_CUDA(cudaMemcpyToSymbol(c_st_dj, dj.data(), sizeof(int) * ctx->st_n));
     ESIMP_CUDA(cudaMemcpyToSymbol(c_st_dk, dk.data(), sizeof(int) * ctx->st_n));
     ESIMP_CUDA(cudaMemcpyToSymbol(c_st_w, ctx->st_w.data(), sizeof(double) * ctx->st_n));
-    g_stencil_owner = ctx;
+    g_stencil_owner[ctx->device & 63] = ctx;
     return ESIMP_OK;
 }
 
@@ -103,7 +105,10 @@ int filter_build_stencil(esimp_ctx* ctx) {
     for (int s = 0; s < ctx->st_n; ++s) ctx->st_halo = std::max(ctx->st_halo, abs(ctx->st_off[3 * s]));
     if (ctx->nranks > 1 && ctx->st_halo > ctx->halo_e)
         return esimp_fail(ctx, ESIMP_ERR_STATE, "filter radius needs more ghost layers than the slab holds");
-    g_stencil_owner = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_const_mutex);
+        g_stencil_owner[ctx->device & 63] = nullptr;
+    }
     ESIMP_TRY(upload_stencil(ctx));
     if (!ctx->d_filtD) ESIMP_CUDA(cudaMalloc(&ctx->d_filtD, sizeof(double) * ctx->ncell_loc));
     LAUNCH_STREAM(k_filter_D, ctx->g, ctx->st_n, ctx->hx * ctx->hy * ctx->hz, ctx->d_filtD, (long long)ctx->ncell_loc);

@@ -30,8 +30,8 @@ __constant__ double c_K0[24 * 24];  // dense unit-modulus element matrix, local 
 __constant__ double c_B[8][3][3];   // mode-space blocks per parity class
 __constant__ float c_Bf[8][3][3];   // the same in single precision (FP32 multigrid cycle, multigrid32.cu)
 __constant__ double c_kdiag[3];     // K0[3a+c,3a+c] (same for every node a of a cuboid)
-static const esimp_ctx* g_const_owner = nullptr;
-static const esimp_ctx* g_const_owner_f32 = nullptr;  // owner of c_Bf (uploaded only when the FP32 cycle is used)
+static const esimp_ctx* g_const_owner[64] = {};  // per device
+static const esimp_ctx* g_const_owner_f32[64] = {};  // per device  // owner of c_Bf (uploaded only when the FP32 cycle is used)
 
 #include "fused_kernel.cuh"
 #include "sweep_kernel.cuh"
@@ -116,12 +116,14 @@ void tet4_element_matrix(const double* xyz, double lam, double mu, double* ke) {
 
 // a destroyed context must not be mistaken for the owner of the constants by a later one at the same address
 void hex8_forget_ctx(const esimp_ctx* ctx) {
-    if (g_const_owner == ctx) g_const_owner = nullptr;
-    if (g_const_owner_f32 == ctx) g_const_owner_f32 = nullptr;
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    if (g_const_owner[ctx->device & 63] == ctx) g_const_owner[ctx->device & 63] = nullptr;
+    if (g_const_owner_f32[ctx->device & 63] == ctx) g_const_owner_f32[ctx->device & 63] = nullptr;
 }
 
 // Build K0 (unit modulus), its mode-space blocks and the nodal diagonal for the context's cuboid.
 int hex8_upload_constants(esimp_ctx* ctx) {
+    std::lock_guard<std::mutex> lock(g_const_mutex);
     if (!ctx->k0_valid) {
         const double nu = ctx->prm.nu;
         const double lam = nu / ((1 + nu) * (1 - 2 * nu)), mu = 1.0 / (2 * (1 + nu));  // SensitivityAnalysis.jl:44-45
@@ -137,7 +139,7 @@ int hex8_upload_constants(esimp_ctx* ctx) {
         for (int a = 0; a < 8; ++a)
             for (int m = 0; m < 8; ++m)
                 H[a][m] = ((m & 1) ? HEXREF[a][0] : 1.0) * ((m & 2) ? HEXREF[a][1] : 1.0) * ((m & 4) ? HEXREF[a][2] : 1.0);
-        static double Kt[24][24];
+        double Kt[24][24];
         double kmax = 0;
         for (int m1 = 0; m1 < 8; ++m1)
             for (int c = 0; c < 3; ++c)
@@ -162,13 +164,13 @@ int hex8_upload_constants(esimp_ctx* ctx) {
                 for (int d = 0; d < 3; ++d) ctx->B[q][c][d] = pat(q, c, d) ? Kt[3 * (q ^ (1 << c)) + c][3 * (q ^ (1 << d)) + d] : 0.0;
         for (int c = 0; c < 3; ++c) ctx->kdiag[c] = ctx->K0[c * 24 + c];
         ctx->k0_valid = true;
-        g_const_owner = nullptr;
+        g_const_owner[ctx->device & 63] = nullptr;
     }
-    if (g_const_owner != ctx) {
+    if (g_const_owner[ctx->device & 63] != ctx) {
         ESIMP_CUDA(cudaMemcpyToSymbolAsync(c_K0, ctx->K0, sizeof(ctx->K0), 0, cudaMemcpyHostToDevice, ctx->stream));
         ESIMP_CUDA(cudaMemcpyToSymbolAsync(c_B, ctx->B, sizeof(ctx->B), 0, cudaMemcpyHostToDevice, ctx->stream));
         ESIMP_CUDA(cudaMemcpyToSymbolAsync(c_kdiag, ctx->kdiag, sizeof(ctx->kdiag), 0, cudaMemcpyHostToDevice, ctx->stream));
-        g_const_owner = ctx;
+        g_const_owner[ctx->device & 63] = ctx;
     }
     return ESIMP_OK;
 }
@@ -255,7 +257,7 @@ static int launch_fused_tt(esimp_ctx* ctx, const OpView& vw, const T* E_t, bool 
     RedOut<1> dot_out{{ctx->d_scal + (DOT ? dot_slot : 0)}};
     // only fine-grid applies are timed (multigrid levels reuse this kernel on coarser grids)
     // every fine-grid launch is timed; tag 0 = plain / dot applies (the roofline number), 1 = fused smoother / residual modes
-    const bool timed = ctx->prof_on && fine && 2 * ctx->prof_n + 1 < (int)ctx->prof_ev.size();
+    const bool timed = ctx->prof_on >= (MODE <= FUSE_DOT ? 1 : 2) && fine && 2 * ctx->prof_n + 1 < (int)ctx->prof_ev.size();
     if (timed) ctx->prof_tag[ctx->prof_n] = MODE <= FUSE_DOT ? PROF_OP_PLAIN : (MODE == FUSE_RESID ? PROF_OP_RESID : PROF_OP_SMOOTH);
     if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
     kern<<<grid, block, smem, ctx->stream>>>(g, vw.mv_e0, vw.mv_e1, vw.own_p0, vw.own_p1, chunk, E_t, d_in, d_out,
@@ -381,7 +383,7 @@ static int launch_sweep_r(esimp_ctx* ctx, const OpView& vw, bool fine, const dou
         ESIMP_TRY(make_map3(ctx, &tmOp[b], ops[b], nz1, ny1, n3, g.nzp, g.plane, 32, SW_OROWS, 3));
         ESIMP_TRY(make_map3(ctx, &tmOpx[b], ops[b], nz1, ny1, n3, g.nzp, g.plane, 2, SW_OROWS, 3));
     }
-    const bool timed = ctx->prof_on && fine && 2 * ctx->prof_n + 1 < (int)ctx->prof_ev.size();
+    const bool timed = ctx->prof_on >= (MODE <= FUSE_DOT ? 1 : 2) && fine && 2 * ctx->prof_n + 1 < (int)ctx->prof_ev.size();
     if (timed) ctx->prof_tag[ctx->prof_n] = MODE <= FUSE_DOT ? PROF_OP_PLAIN : (MODE == FUSE_RESID ? PROF_OP_RESID : PROF_OP_SMOOTH);
     if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
     kern<<<dim3(nty, nchunk), SW_THREADS, smem, ctx->stream>>>(a, tmU, tmE, tmOp[0], tmOp[1], tmOp[2], tmOpx[0], tmOpx[1], tmOpx[2]);
@@ -480,14 +482,15 @@ int hex8_resid_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double
 static int upload_constants_f32(esimp_ctx* ctx) {
     const bool stale = !ctx->k0_valid;  // hex8_upload_constants recomputes B then
     ESIMP_TRY(hex8_upload_constants(ctx));
-    if (stale || g_const_owner_f32 != ctx) {
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    if (stale || g_const_owner_f32[ctx->device & 63] != ctx) {
         float Bf[8][3][3];
         for (int q = 0; q < 8; ++q)
             for (int c = 0; c < 3; ++c)
                 for (int d = 0; d < 3; ++d) Bf[q][c][d] = (float)ctx->B[q][c][d];
         // stream ordered like the FP64 constants; a pageable source is staged before the call returns, so a local is fine
         ESIMP_CUDA(cudaMemcpyToSymbolAsync(c_Bf, Bf, sizeof(Bf), 0, cudaMemcpyHostToDevice, ctx->stream));
-        g_const_owner_f32 = ctx;
+        g_const_owner_f32[ctx->device & 63] = ctx;
     }
     return ESIMP_OK;
 }

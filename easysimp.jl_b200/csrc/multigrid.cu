@@ -641,7 +641,7 @@ static int mg_vcycle(esimp_ctx* ctx, int l, bool first_done = false, int dot_slo
         LAUNCH_STREAM(k_residual, L.d_r, L.d_q, L.own_dof0, L.own_dof1);
     }
     // PROF_MG_COARSE: from the exchange of the fine residual to the end of the prolongation, one pair per V-cycle
-    const bool time_coarse = l == 0 && ctx->prof_on && !ctx->prof_coarse_pending && ctx->prof_coarse_ev[0];
+    const bool time_coarse = l == 0 && ctx->prof_on >= 2 && !ctx->prof_coarse_pending && ctx->prof_coarse_ev[0];
     if (time_coarse) cudaEventRecord(ctx->prof_coarse_ev[0], ctx->stream);
     if (ctx->nranks > 1) ESIMP_TRY(comm_halo_nodes_lv(ctx, L.vw.g, L.vw.own_p0, L.vw.own_p1, L.has_left, L.has_right, L.d_q));
     if (C.replicated && !L.replicated) {
@@ -709,7 +709,7 @@ struct HostPcgClock {  // PROF_HOST_PCG / PROF_HOST_WAIT: wall time of the solve
     int fetches = 0;
     explicit HostPcgClock(esimp_ctx* c) : ctx(c) {}
     ~HostPcgClock() {
-        if (!ctx->prof_on) return;
+        if (ctx->prof_on < 2) return;
         ctx->prof_ms_cat[PROF_HOST_PCG] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         ctx->prof_cnt_cat[PROF_HOST_PCG] += 1;
         ctx->prof_ms_cat[PROF_HOST_WAIT] += wait_ms;

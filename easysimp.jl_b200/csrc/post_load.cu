@@ -23,10 +23,11 @@
 #include "stress_math.cuh"
 
 __constant__ double c_gradN[8][8][3];  // [gauss point][node][d/dx_d], cuboid hx*hy*hz, VTK node order
-static const esimp_ctx* g_grad_owner = nullptr;
+static const esimp_ctx* g_grad_owner[64] = {};  // per device
 
 void post_forget_ctx(const esimp_ctx* ctx) {
-    if (g_grad_owner == ctx) g_grad_owner = nullptr;
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    if (g_grad_owner[ctx->device & 63] == ctx) g_grad_owner[ctx->device & 63] = nullptr;
 }
 
 #define LAUNCH_STREAM(kern, ...)                                        \
@@ -37,11 +38,12 @@ void post_forget_ctx(const esimp_ctx* ctx) {
     } while (0)
 
 static int upload_gradients(esimp_ctx* ctx) {
-    if (g_grad_owner == ctx) return ESIMP_OK;
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    if (g_grad_owner[ctx->device & 63] == ctx) return ESIMP_OK;
     double G[8][8][3];
     cuboid_gradient_table(ctx->hx, ctx->hy, ctx->hz, G);
     ESIMP_CUDA(cudaMemcpyToSymbol(c_gradN, G, sizeof(G)));
-    g_grad_owner = ctx;
+    g_grad_owner[ctx->device & 63] = ctx;
     return ESIMP_OK;
 }
 

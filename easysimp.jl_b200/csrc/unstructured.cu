@@ -316,9 +316,10 @@ int um_build(esimp_ctx* ctx, int celltype, int64_t n_cells, int64_t n_nodes, con
     return ESIMP_OK;
 }
 
-static const esimp_ctx* g_um_dn_owner = nullptr;
+static const esimp_ctx* g_um_dn_owner[64] = {};  // per device
 static int um_upload_reference_gradients(esimp_ctx* ctx) {
-    if (g_um_dn_owner == ctx) return ESIMP_OK;
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    if (g_um_dn_owner[ctx->device & 63] == ctx) return ESIMP_OK;
     static const double R[8][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {1, 1, 1}, {-1, 1, 1}};
     double dN[8][8][3];
     const double gp = 1.0 / sqrt(3.0);
@@ -333,11 +334,12 @@ static int um_upload_reference_gradients(esimp_ctx* ctx) {
     }
     ESIMP_CUDA(cudaMemcpyToSymbolAsync(c_um_dN, dN, sizeof(dN), 0, cudaMemcpyHostToDevice, ctx->stream));
     ESIMP_CUDA(cudaStreamSynchronize(ctx->stream));  // dN is a stack array
-    g_um_dn_owner = ctx;
+    g_um_dn_owner[ctx->device & 63] = ctx;
     return ESIMP_OK;
 }
 void um_forget_ctx(const esimp_ctx* ctx) {
-    if (g_um_dn_owner == ctx) g_um_dn_owner = nullptr;
+    std::lock_guard<std::mutex> lock(g_const_mutex);
+    if (g_um_dn_owner[ctx->device & 63] == ctx) g_um_dn_owner[ctx->device & 63] = nullptr;
 }
 
 template <int ND>

@@ -357,7 +357,9 @@ class Context:
         assert k.size == self.n_cells
         self._chk(self.lib.esimp_set_design(self._h, p), "esimp_set_design")
 
-    def profile_enable(self, on=True):
+    def profile_enable(self, on=2):
+        """0 off, 1 = clock the plain / dot operator launches only, 2 (or True... = 1!) every kernel category; pass the level as an int."""
+        on = 2 if on is True else int(on)
         self._chk(self.lib.esimp_profile_enable(self._h, int(on)), "esimp_profile_enable")
 
     def profile_matvec(self):

@@ -222,6 +222,9 @@ int esimp_bench_operator_mode(esimp_ctx* ctx, int mode, int reps, double* ms_avg
 /* in-region timing: while enabled, every launch of the structured operator kernel is bracketed by
  * CUDA events on the context's stream; esimp_profile_matvec returns the summed kernel time, the number
  * of timed launches and the algorithmic bytes one launch moves on this rank. */
+/* on = 1: only the plain / plain + dot operator launches are clocked (about 50 event pairs per SIMP step: cheap enough to stay
+ * inside a timed region); on = 2: every category of esimp_profile_kernels as well (thousands of event pairs per step -- costs a few
+ * per cent where the step is latency bound, N >= 4 GPUs); 0 = off */
 int esimp_profile_enable(esimp_ctx* ctx, int on);
 int esimp_profile_matvec(esimp_ctx* ctx, double* ms_sum, int64_t* count, double* bytes_per_apply);
 /* same clock over EVERY fine-grid launch of the operator kernel, including the modes that fuse the multigrid smoother
