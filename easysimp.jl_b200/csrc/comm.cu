@@ -9,6 +9,7 @@
 // libnccl.so.2 is dlopen'ed lazily (the copy torch already loaded is reused when the host process
 // imported torch first), so single-GPU users never need NCCL installed.
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>
 
 #include "ctx.cuh"
@@ -117,8 +118,8 @@ int comm_init(esimp_ctx* ctx, int rank, int nranks, const void* id128) {
 
 void comm_destroy(esimp_ctx* ctx) {
     for (int s = 0; s < 2; ++s) {
-        if (ctx->p2p_peer_mail[s]) cudaIpcCloseMemHandle(ctx->p2p_peer_mail[s]);
-        if (ctx->p2p_peer_flags[s]) cudaIpcCloseMemHandle(ctx->p2p_peer_flags[s]);
+        if (ctx->p2p_peer_mail[s] && !ctx->p2p_same_process) cudaIpcCloseMemHandle(ctx->p2p_peer_mail[s]);
+        if (ctx->p2p_peer_flags[s] && !ctx->p2p_same_process) cudaIpcCloseMemHandle(ctx->p2p_peer_flags[s]);
         ctx->p2p_peer_mail[s] = nullptr;
         ctx->p2p_peer_flags[s] = nullptr;
     }
@@ -232,15 +233,21 @@ int comm_p2p_setup(esimp_ctx* ctx, long long plane_doubles) {
     struct Rec {
         cudaIpcMemHandle_t mail, flags;
         int ok, device;
+        long long pid;                  // ranks of ONE process (esimp_multi) share an address space: plain peer access, no IPC
+        double* mail_ptr;
+        unsigned long long* flags_ptr;
     };
     Rec mine{};
     mine.ok = 1;
     mine.device = ctx->device;
+    mine.pid = (long long)getpid();
     if (cudaMalloc(&ctx->p2p_mail, sizeof(double) * 4 * ctx->p2p_plane_cap) != cudaSuccess ||
         cudaMalloc(&ctx->p2p_flags, sizeof(unsigned long long) * 8) != cudaSuccess)
         mine.ok = 0;
     if (mine.ok) {
         cudaMemset(ctx->p2p_flags, 0, sizeof(unsigned long long) * 8);
+        mine.mail_ptr = ctx->p2p_mail;
+        mine.flags_ptr = ctx->p2p_flags;
         if (cudaIpcGetMemHandle(&mine.mail, ctx->p2p_mail) != cudaSuccess || cudaIpcGetMemHandle(&mine.flags, ctx->p2p_flags) != cudaSuccess) mine.ok = 0;
     }
     cudaGetLastError();
@@ -263,6 +270,15 @@ int comm_p2p_setup(esimp_ctx* ctx, long long plane_doubles) {
             if (q < 0 || q >= R) continue;
             int can = 0;
             if (all[q].device != ctx->device) cudaDeviceCanAccessPeer(&can, ctx->device, all[q].device);
+            if (can && all[q].pid == mine.pid) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(all[q].device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) local_fail = 1;
+                cudaGetLastError();
+                ctx->p2p_peer_mail[s] = all[q].mail_ptr;
+                ctx->p2p_peer_flags[s] = all[q].flags_ptr;
+                ctx->p2p_same_process = true;
+                continue;
+            }
             if (!can || cudaIpcOpenMemHandle((void**)&ctx->p2p_peer_mail[s], all[q].mail, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess ||
                 cudaIpcOpenMemHandle((void**)&ctx->p2p_peer_flags[s], all[q].flags, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess)
                 local_fail = 1;

@@ -103,6 +103,7 @@ struct esimp_ctx {
     // and one flag block, both mapped into the x-neighbours through CUDA IPC; a single kernel pushes the boundary planes over NVLink,
     // signals, waits for the neighbours' signal and unpacks.  p2p = 0: not set up (NCCL send / recv), 1: active, -1: unavailable
     int p2p = 0;
+    bool p2p_same_process = false;  // neighbours are contexts of this process (esimp_multi): raw peer pointers, nothing to close
     double* p2p_mail = nullptr;               // [side from: 0 left, 1 right][parity][p2p_plane_cap]
     unsigned long long* p2p_flags = nullptr;  // [0] epoch written by the left neighbour, [1] by the right one, [2] CTA ticket, [3] timeouts
     double* p2p_peer_mail[2] = {nullptr, nullptr};               // the left / right neighbour's mailbox (IPC mappings)

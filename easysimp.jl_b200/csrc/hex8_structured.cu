@@ -23,6 +23,8 @@
 
 #include <type_traits>
 
+#include <atomic>
+
 #include "ctx.cuh"
 
 // ---------------------------------------------------------------------------- constants
@@ -236,12 +238,12 @@ static int launch_fused_tt(esimp_ctx* ctx, const OpView& vw, const T* E_t, bool 
     if (ctx->fused_chunk > 0) chunk = ctx->fused_chunk;
     const int nchunk = (nplanes + chunk - 1) / chunk;
     const size_t smem = sizeof(FusedSmem<T, TY, TZ, (MODE == FUSE_SMOOTH || MODE == FUSE_SMOOTH_DOT) ? 3 : (MODE == FUSE_RESID ? 1 : 0)>);
-    static unsigned long long attr_devices = 0;  // the attribute is per device: one bit per device this process has used
+    static std::atomic<unsigned long long> attr_devices{0};  // the attribute is per device: one bit per device this process has used
     auto kern = k_matvec_fused<T, TY, TZ, ATOMIC, MINB, MODE>;
     const unsigned long long dev_bit = 1ull << (ctx->device & 63);
-    if (!(attr_devices & dev_bit)) {
+    if (!(attr_devices.load() & dev_bit)) {
         ESIMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_devices |= dev_bit;
+        attr_devices.fetch_or(dev_bit);
     }
     if constexpr (ATOMIC && std::is_same<T, double>::value) {
         k_zero_perimeter<TY, TZ><<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(g, vw.own_p0, vw.own_p1, d_out);
@@ -341,12 +343,12 @@ static int launch_sweep_r(esimp_ctx* ctx, const OpView& vw, bool fine, const dou
     if (ctx->fused_chunk > 0) chunk = std::min(ctx->fused_chunk, std::max(1, max_chunk));
     const int nchunk = (nplanes + chunk - 1) / chunk;
     const size_t smem = sizeof(Smem) + (size_t)(chunk + 3) * SW_CARRY_ROW * 8;
-    static unsigned long long attr_devices = 0;
+    static std::atomic<unsigned long long> attr_devices{0};
     auto kern = k_matvec_sweep<MODE, RING>;
     const unsigned long long dev_bit = 1ull << (ctx->device & 63);
-    if (!(attr_devices & dev_bit)) {
+    if (!(attr_devices.load() & dev_bit)) {
         ESIMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
-        attr_devices |= dev_bit;
+        attr_devices.fetch_or(dev_bit);
     }
     SweepArgs a{};
     a.g = g;

@@ -29,6 +29,8 @@
 
 #include <chrono>
 
+#include <atomic>
+
 #include "ctx.cuh"
 #include "coarse_tail.cuh"
 
@@ -607,11 +609,11 @@ static int mg_tail_cycle(esimp_ctx* ctx) {
     }
     long long sdbl = 0;
     for (int l = t; l < n; ++l) sdbl = std::max(sdbl, coarse_tail_slab_doubles(ctx->mg[l].vw.g.nx, ctx->mg[l].vw.g.ny, ctx->mg[l].vw.g.nz));
-    static unsigned long long attr_devices = 0;
+    static std::atomic<unsigned long long> attr_devices{0};
     const unsigned long long dev_bit = 1ull << (ctx->device & 63);
-    if (!(attr_devices & dev_bit)) {
+    if (!(attr_devices.load() & dev_bit)) {
         ESIMP_CUDA(cudaFuncSetAttribute(k_coarse_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr_devices |= dev_bit;
+        attr_devices.fetch_or(dev_bit);
     }
     k_coarse_tail<<<CT_CTAS, CT_THREADS, (size_t)sdbl * 8, ctx->stream>>>(a);
     ctx->launches++;

@@ -95,6 +95,26 @@ _SIGNATURES = {
     "esimp_stress_fields": (C.c_int, [_P, _D, _D, _D, _D, _I64]),
     "esimp_stress_tensors": (C.c_int, [_P, C.c_int64, C.c_int64, _D]),
     "esimp_stress_nq": (C.c_int, [_P]),
+    "esimp_multi_create": (C.c_int, [C.POINTER(_P), C.POINTER(C.c_int), C.c_int]),
+    "esimp_multi_destroy": (C.c_int, [_P]),
+    "esimp_multi_last_error": (C.c_char_p, [_P]),
+    "esimp_multi_n_gpus": (C.c_int, [_P]),
+    "esimp_multi_rank_ctx": (_P, [_P, C.c_int]),
+    "esimp_multi_n_dofs": (C.c_int64, [_P]),
+    "esimp_multi_n_cells": (C.c_int64, [_P]),
+    "esimp_multi_set_params": (C.c_int, [_P, C.POINTER(EsimpParams)]),
+    "esimp_multi_set_grid_structured": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, _I64]),
+    "esimp_multi_set_dirichlet": (C.c_int, [_P, _I64, C.c_int64]),
+    "esimp_multi_set_load": (C.c_int, [_P, _D]),
+    "esimp_multi_set_body_force": (C.c_int, [_P, _D, C.c_double]),
+    "esimp_multi_filter_build_structured": (C.c_int, [_P]),
+    "esimp_multi_init_design": (C.c_int, [_P, _D]),
+    "esimp_multi_set_design": (C.c_int, [_P, _D]),
+    "esimp_multi_iterate": (C.c_int, [_P, C.POINTER(EsimpIterStats)]),
+    "esimp_multi_final_analysis": (C.c_int, [_P, _D, _D, C.POINTER(C.c_int)]),
+    "esimp_multi_get_design": (C.c_int, [_P, _D]),
+    "esimp_multi_get_physical_density": (C.c_int, [_P, _D]),
+    "esimp_multi_get_displacement": (C.c_int, [_P, _D]),
 }
 
 _lib = None
@@ -407,3 +427,113 @@ def comm_unique_id() -> bytes:
     if st < 0:
         raise EsimpError(f"esimp_comm_unique_id failed: {lib.esimp_last_error(None).decode()}")
     return buf.raw
+
+
+class MultiContext:
+    """esimp_multi*: N GPUs driven from this one process (one host thread per GPU inside the library).  Same global host arrays as
+    Context; only the loop-path calls exist here, `rank_ctx` exposes a rank's own esimp_ctx* for anything else."""
+
+    def __init__(self, devices=None, n_gpus=None):
+        self.lib = load_library()
+        self._h = _P()
+        if devices is None:
+            n = int(n_gpus)
+            arr = None
+        else:
+            n = len(devices)
+            arr = (C.c_int * n)(*devices)
+        st = self.lib.esimp_multi_create(C.byref(self._h), arr, n)
+        if st < 0:
+            raise EsimpError(f"esimp_multi_create failed ({st}): {self.lib.esimp_multi_last_error(None).decode()}")
+        self.params = EsimpParams()
+        self.lib.esimp_default_params(C.byref(self.params))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.esimp_multi_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def _chk(self, st, what):
+        if st < 0:
+            raise EsimpError(f"{what} failed ({st}): {self.lib.esimp_multi_last_error(self._h).decode()}")
+        return st
+
+    @property
+    def n_gpus(self):
+        return self.lib.esimp_multi_n_gpus(self._h)
+
+    @property
+    def n_dofs(self):
+        return self.lib.esimp_multi_n_dofs(self._h)
+
+    @property
+    def n_cells(self):
+        return self.lib.esimp_multi_n_cells(self._h)
+
+    def set_params(self, **kw):
+        for k, v in kw.items():
+            if not hasattr(self.params, k):
+                raise AttributeError(k)
+            setattr(self.params, k, v)
+        self._chk(self.lib.esimp_multi_set_params(self._h, C.byref(self.params)), "esimp_multi_set_params")
+
+    def set_grid_structured(self, nx, ny, nz, hx, hy, hz, dof_of_node=None):
+        ptr = None
+        if dof_of_node is not None:
+            keep, ptr = _i64(np.asarray(dof_of_node).reshape(-1))
+        self._chk(self.lib.esimp_multi_set_grid_structured(self._h, nx, ny, nz, hx, hy, hz, ptr), "esimp_multi_set_grid_structured")
+
+    def set_dirichlet(self, dofs):
+        keep, ptr = _i64(dofs)
+        self._chk(self.lib.esimp_multi_set_dirichlet(self._h, ptr, len(keep)), "esimp_multi_set_dirichlet")
+
+    def set_load(self, f):
+        keep, ptr = _f64(f)
+        self._chk(self.lib.esimp_multi_set_load(self._h, ptr), "esimp_multi_set_load")
+
+    def set_body_force(self, accel, base_density=1.0):
+        if accel is None:
+            self._chk(self.lib.esimp_multi_set_body_force(self._h, None, 0.0), "esimp_multi_set_body_force")
+        else:
+            keep, ptr = _f64(accel)
+            self._chk(self.lib.esimp_multi_set_body_force(self._h, ptr, float(base_density)), "esimp_multi_set_body_force")
+
+    def filter_build_structured(self):
+        self._chk(self.lib.esimp_multi_filter_build_structured(self._h), "esimp_multi_filter_build_structured")
+
+    def init_design(self, rho=None):
+        ptr = None
+        if rho is not None:
+            keep, ptr = _f64(rho)
+        self._chk(self.lib.esimp_multi_init_design(self._h, ptr), "esimp_multi_init_design")
+
+    def set_design(self, rho):
+        keep, ptr = _f64(rho)
+        self._chk(self.lib.esimp_multi_set_design(self._h, ptr), "esimp_multi_set_design")
+
+    def iterate(self):
+        st = EsimpIterStats()
+        self._chk(self.lib.esimp_multi_iterate(self._h, C.byref(st)), "esimp_multi_iterate")
+        return st
+
+    def final_analysis(self):
+        e, v, it = C.c_double(0), C.c_double(0), C.c_int(0)
+        self._chk(self.lib.esimp_multi_final_analysis(self._h, C.byref(e), C.byref(v), C.byref(it)), "esimp_multi_final_analysis")
+        return e.value, v.value, it.value
+
+    def get_design(self):
+        rho = np.zeros(self.n_cells)
+        self._chk(self.lib.esimp_multi_get_design(self._h, rho.ctypes.data_as(_D)), "esimp_multi_get_design")
+        return rho
+
+    def get_physical_density(self):
+        rho = np.zeros(self.n_cells)
+        self._chk(self.lib.esimp_multi_get_physical_density(self._h, rho.ctypes.data_as(_D)), "esimp_multi_get_physical_density")
+        return rho
+
+    def get_displacement(self):
+        u = np.zeros(self.n_dofs)
+        self._chk(self.lib.esimp_multi_get_displacement(self._h, u.ctypes.data_as(_D)), "esimp_multi_get_displacement")
+        return u

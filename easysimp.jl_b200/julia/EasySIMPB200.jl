@@ -410,10 +410,100 @@ function simp_optimize(grid::Grid, dh::DofHandler, cellvalues, loads, boundary_c
     return OptimizationResult(rho, u, stresses, e[], v[], iteration, converged, energy_history, volume_history)
 end
 
+# ---- N GPUs from this one Julia session (include/easysimp_b200.h, esimp_multi_*; SURVEY 8b) --------------------------------
+# The reference is a single process (Optimization.jl:178).  An esimp_multi owns one context per device, the NCCL communicator
+# and the x-slab partition; every call takes the same GLOBAL arrays as the one-GPU path and fans out to one host thread per GPU
+# inside the library, so no MPI launcher is needed.  Structured generate_grid meshes only (imported meshes run as replicas).
+mutable struct MultiContext
+    ptr::Ptr{Cvoid}
+    function MultiContext(devices::AbstractVector{<:Integer})
+        r = Ref{Ptr{Cvoid}}(C_NULL)
+        dev = Cint.(collect(devices))
+        st = ccall((:esimp_multi_create, LIB), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cint}, Cint), r, dev, length(dev))
+        st < 0 && error("esimp_multi_create: " * unsafe_string(ccall((:esimp_multi_last_error, LIB), Cstring, (Ptr{Cvoid},), C_NULL)))
+        m = new(r[])
+        finalizer(c -> (c.ptr != C_NULL && ccall((:esimp_multi_destroy, LIB), Cint, (Ptr{Cvoid},), c.ptr); c.ptr = C_NULL), m)
+        return m
+    end
+end
+function check(m::MultiContext, st::Integer, what)
+    st < 0 && error("$what failed ($st): " * unsafe_string(ccall((:esimp_multi_last_error, LIB), Cstring, (Ptr{Cvoid},), m.ptr)))
+    return st
+end
+
+"""
+    simp_optimize_multi(grid, dh, cellvalues, loads, boundary_conditions, params, acceleration_data = nothing;
+                        devices = 0:7, pcg_rtol = 1e-8, pcg_maxit = 200000)
+
+`simp_optimize` (Optimization.jl:178-565) on several GPUs of one node: same arguments, console lines, logger and
+`OptimizationResult`; the loop body is one `esimp_multi_iterate` per iteration.  The `stresses` Dict of the result is empty and
+the per-iteration export branches are not wired (use the one-GPU entry point for those, or `esimp_multi_rank_ctx` + the stage calls).
+"""
+function simp_optimize_multi(grid::Grid, dh::DofHandler, cellvalues, loads, boundary_conditions, params::OptimizationParameters,
+                             acceleration_data = nothing; devices = 0:7, pcg_rtol::Float64 = 1e-8, pcg_maxit::Integer = 200000)
+    sd = structured_dims(grid)
+    sd === nothing && error("simp_optimize_multi needs a generate_grid hexahedral mesh (imported meshes are not partitioned)")
+    println("Starting SIMP topology optimization (B200 backend, $(length(devices)) GPUs)")
+    logger = isempty(params.export_path) ? nothing : OptimizationLogger(params.export_path, params.task_name)
+    m = MultiContext(devices)
+    R = params.filter_radius * characteristic_size(grid)
+    prm = EsimpParams(params.E0, params.Emin, params.ν, params.p, params.volume_fraction, params.move_limit, params.damping, R,
+                      params.filter_type == :density ? 1 : 0, Int32(pcg_maxit), pcg_rtol, Int32(25), 0, 1, 1)   # multigrid-preconditioned CG
+    check(m, ccall((:esimp_multi_set_params, LIB), Cint, (Ptr{Cvoid}, Ref{EsimpParams}), m.ptr, prm), "esimp_multi_set_params")
+    check(m, ccall((:esimp_multi_set_grid_structured, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Cint, Cdouble, Cdouble, Cdouble, Ptr{Int64}),
+                   m.ptr, Int(sd[1]), Int(sd[2]), Int(sd[3]), sd[4], sd[5], sd[6], dof_of_node(dh)), "esimp_multi_set_grid_structured")
+    check(m, ccall((:esimp_multi_filter_build_structured, LIB), Cint, (Ptr{Cvoid},), m.ptr), "esimp_multi_filter_build_structured")
+    prescribed = Int64.(unique(reduce(vcat, [ch.prescribed_dofs for ch in boundary_conditions]; init = Int[]))) .- 1
+    check(m, ccall((:esimp_multi_set_dirichlet, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int64), m.ptr, prescribed, length(prescribed)),
+          "esimp_multi_set_dirichlet")
+    f = zeros(ndofs(dh))
+    foreach(l -> apply_load_condition!(f, l), loads)
+    check(m, ccall((:esimp_multi_set_load, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), m.ptr, f), "esimp_multi_set_load")
+    if acceleration_data !== nothing
+        acc, base = acceleration_data
+        check(m, ccall((:esimp_multi_set_body_force, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Cdouble), m.ptr,
+                       Float64[acc[1], acc[2], acc[3]], Float64(base)), "esimp_multi_set_body_force")
+    end
+    check(m, ccall((:esimp_multi_init_design, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), m.ptr, C_NULL), "esimp_multi_init_design")
+    n_cells, n_dofs = getncells(grid), ndofs(dh)
+    total_volume = n_cells * sd[4] * sd[5] * sd[6]
+    energy_history, volume_history = Float64[], Float64[]
+    converged, iteration = false, 0
+    stats = Ref{EsimpIterStats}()
+    for iter in 1:params.max_iterations
+        iteration = iter
+        check(m, ccall((:esimp_multi_iterate, LIB), Cint, (Ptr{Cvoid}, Ref{EsimpIterStats}), m.ptr, stats), "esimp_multi_iterate")
+        s = stats[]
+        push!(energy_history, s.energy); push!(volume_history, s.volume)
+        vf = s.volume / total_volume
+        logger !== nothing && log_iteration!(logger, iter, s.energy, vf, s.change, s.lambda, s.grayness, s.max_u)
+        @printf("Iter %4d | Energy: %.4e | Vol.Frac: %.4f | Change: %.4e\n", iter, s.energy, vf, s.change)
+        if s.change < params.tolerance
+            converged = true
+            println("Converged at iteration $(iter) with change $(s.change)")
+            break
+        end
+    end
+    e, v, its = Ref{Cdouble}(0), Ref{Cdouble}(0), Ref{Cint}(0)
+    check(m, ccall((:esimp_multi_final_analysis, LIB), Cint, (Ptr{Cvoid}, Ref{Cdouble}, Ref{Cdouble}, Ref{Cint}), m.ptr, e, v, its),
+          "esimp_multi_final_analysis")
+    rho = zeros(n_cells); u = zeros(n_dofs)
+    check(m, ccall((:esimp_multi_get_physical_density, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), m.ptr, rho), "esimp_multi_get_physical_density")
+    check(m, ccall((:esimp_multi_get_displacement, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), m.ptr, u), "esimp_multi_get_displacement")
+    if logger !== nothing
+        write_summary(logger, e[], v[], converged)
+        close_logger(logger)
+    end
+    println("Optimization completed")
+    println("Final energy: $(e[])")
+    println("Final volume fraction: $(v[] / total_volume)")
+    return OptimizationResult(rho, u, Dict{Int,Vector{SymmetricTensor{2,3,Float64}}}(), e[], v[], iteration, converged, energy_history, volume_history)
+end
+
 "the round-1 name of the entry point"
 simp_optimize_b200(args...; kwargs...) = simp_optimize(args...; kwargs...)
 
 export Context, B200Operator, setup_problem_b200, apply_fixed_boundary!, apply_sliding_boundary!, assemble_stiffness_matrix_simp!,
-       simp_optimize, simp_optimize_b200, stress_fields_b200, stress_dict_b200
+       simp_optimize, simp_optimize_b200, simp_optimize_multi, MultiContext, stress_fields_b200, stress_dict_b200
 
 end # module

@@ -211,6 +211,35 @@ int esimp_set_design(esimp_ctx* ctx, const double* rho);
 int64_t esimp_n_dofs(const esimp_ctx* ctx);
 int64_t esimp_n_cells(const esimp_ctx* ctx);
 
+/* ---- multi-GPU from ONE process (the reference is a single Julia session, Optimization.jl:178) ----------------
+ * An esimp_multi owns one context per device, an NCCL communicator initialised from N threads of this process and the x-slab
+ * partition; every call below takes the same GLOBAL host arrays as its esimp_* namesake and fans out to one host thread per
+ * GPU.  devices = NULL: devices 0 .. n_devices-1.  The scalars of esimp_iter_stats are allreduced inside the library (identical
+ * on every GPU), its phase timers are those of the slowest GPU.  esimp_multi_rank_ctx exposes a rank's own context for the stage
+ * calls that have no multi wrapper; calls that contain collectives must then be made on ALL ranks concurrently (one thread each). */
+typedef struct esimp_multi esimp_multi;
+int esimp_multi_create(esimp_multi** out, const int* devices, int n_devices);
+int esimp_multi_destroy(esimp_multi* m);
+const char* esimp_multi_last_error(const esimp_multi* m); /* m may be NULL: last create error */
+int esimp_multi_n_gpus(const esimp_multi* m);
+esimp_ctx* esimp_multi_rank_ctx(esimp_multi* m, int rank);
+int64_t esimp_multi_n_dofs(const esimp_multi* m);
+int64_t esimp_multi_n_cells(const esimp_multi* m);
+int esimp_multi_set_params(esimp_multi* m, const esimp_params* p);
+int esimp_multi_set_grid_structured(esimp_multi* m, int nx, int ny, int nz, double hx, double hy, double hz,
+                                    const int64_t* dof_of_node);
+int esimp_multi_set_dirichlet(esimp_multi* m, const int64_t* dofs, int64_t n);
+int esimp_multi_set_load(esimp_multi* m, const double* f);
+int esimp_multi_set_body_force(esimp_multi* m, const double* accel3, double base_density);
+int esimp_multi_filter_build_structured(esimp_multi* m);
+int esimp_multi_init_design(esimp_multi* m, const double* rho);
+int esimp_multi_set_design(esimp_multi* m, const double* rho);
+int esimp_multi_iterate(esimp_multi* m, esimp_iter_stats* out);
+int esimp_multi_final_analysis(esimp_multi* m, double* energy, double* volume, int* pcg_iters);
+int esimp_multi_get_design(esimp_multi* m, double* rho);
+int esimp_multi_get_physical_density(esimp_multi* m, double* rho);
+int esimp_multi_get_displacement(esimp_multi* m, double* u);
+
 /* ---- measurement helpers (device-resident timing with CUDA events, bench.py) ----------- */
 /* `reps` operator applies on device-resident vectors; ms_avg = mean launch-to-launch time.
  * bytes_per_apply = algorithmic bytes (16*n_dof + 8*n_cell). */
