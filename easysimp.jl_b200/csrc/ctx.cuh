@@ -142,7 +142,10 @@ struct esimp_ctx {
     int mg_lag = -1;
     // levels >= mg_tail_start run inside ONE cluster kernel (coarse_tail.cuh); 0 = none.  ESIMP_MG_TAIL=0 switches the tail off
     int mg_tail = 1, mg_tail_start = 0;
-    long long mg_tail_nodes = 10000;  // largest level (nodes) the tail takes (ESIMP_MG_TAIL_NODES)
+    // largest level (nodes) the tail takes (ESIMP_MG_TAIL_NODES).  10 000 would also take the 32x16x16 level of a 512x256x256 hierarchy, but the
+    // dense node-by-node operator of the tail on 8 SMs is slower there than nine launches of the fused kernel on 148 (ncu: 304 us per
+    // V-cycle for the tail with that level, SIMP step 331.4 ms against 329.3 ms without it)
+    long long mg_tail_nodes = 2000;
     double* d_K0 = nullptr;  // dense 24 x 24 unit element matrix for the tail kernel
     cudaEvent_t lag_ev[2]{};
 
