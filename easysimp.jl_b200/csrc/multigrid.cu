@@ -349,6 +349,13 @@ static int mg_build_levels(esimp_ctx* ctx) {
                     if (!can_split) break;
                 } else {
                     replicated = true;
+                    // a LARGE level replicated only because its layers do not divide by the rank count: correct, but every rank then
+                    // smooths the whole level and the residual sum is a big allreduce -- say so once (nx a multiple of 2^k * ranks avoids it)
+                    if (!can_split && (long long)cx * cy * cz > ctx->mg_replicate_cells && r == 0)
+                        fprintf(stderr,
+                                "[esimp] multigrid level %d (%dx%dx%d cells) cannot be cut into %d x-slabs of whole layers: it and all coarser levels "
+                                "are replicated on every GPU (slower; choose nx as a multiple of %d)\n",
+                                l, cx, cy, cz, R, 2 * R << (l - 1));
                 }
             }
         }

@@ -345,7 +345,8 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
                     const bool plane_ok = lp >= P0 && lp < P1;  // CTA-uniform
                     constexpr bool PRE_DOT = MODE == FUSE_DOT && (SW_PRELOAD & 1) != 0;
                     constexpr bool PRE_SM = TR::SMOOTH && (SW_PRELOAD & 6) != 0;
-                    constexpr int PRE_NROWS = PRE_DOT ? 2 : (PRE_SM ? ((SW_PRELOAD & 4) ? 2 : 1) : 0);  // node rows r < PRE_NROWS are preloaded
+                    constexpr bool PRE_RS = MODE == FUSE_RESID && (SW_PRELOAD & 2) != 0;  // residual mode: r of both node rows (6 doubles)
+                    constexpr int PRE_NROWS = (PRE_DOT || PRE_RS) ? 2 : (PRE_SM ? ((SW_PRELOAD & 4) ? 2 : 1) : 0);  // node rows r < PRE_NROWS are preloaded
                     double pu[2][3], pr[2][3], pdi[2][3], pz2[2][3];
                     const bool last_seg = s == nseg - 1;
                     const bool ext = extra && last_seg && lane == 31;
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
                             yp[off] = znew;
                             if (MODE == FUSE_SMOOTH_DOT) pq[0] = fma(rv, znew, pq[0]);
                         } else if (MODE == FUSE_RESID) {
-                            yp[off] = op[0] - s_val;
+                            yp[off] = (pre && PRE_RS ? pr[r][c] : op[0]) - s_val;
                         } else {
                             yp[off] = s_val;
                             if (MODE == FUSE_DOT) pq[0] = fma(s_val, pre && PRE_DOT ? pu[r][c] : uin[c * SW_ROWS * SW_BOXZ + r * SW_BOXZ + col], pq[0]);
@@ -409,12 +410,13 @@ __global__ void __launch_bounds__(SW_THREADS, 1)
                         }
                     };
                     if (NF > 0 && plane_ok) sw_bar_wait_a(sw_bar_at(b_ffull, fs), fpar);
-                    if (PRE_DOT || PRE_SM) {
+                    if (PRE_DOT || PRE_SM || PRE_RS) {
 #pragma unroll
                         for (int r = 0; r < PRE_NROWS; ++r)
 #pragma unroll
                             for (int c = 0; c < 3; ++c) {
-                                pu[r][c] = uin[c * SW_ROWS * SW_BOXZ + r * SW_BOXZ];
+                                if (!PRE_RS) pu[r][c] = uin[c * SW_ROWS * SW_BOXZ + r * SW_BOXZ];
+                                if (PRE_RS) pr[r][c] = fzp[c * SW_OROWS * 32 + r * 32];
                                 if (PRE_SM) {
                                     const double* op = fzp + c * SW_OROWS * 32 + r * 32;
                                     pr[r][c] = op[0];
