@@ -504,8 +504,9 @@ def run_b200(args):
         # algorithmic bytes per launch of the other fine-grid kernels on this rank (SURVEY 8d conventions)
         n_cell_r = nx * ny * nz / world
         n_dof_r = (mv_bytes - 8.0 * n_cell_r) / 16.0 if mv_bytes else 3.0 * (nx + 1) * (ny + 1) * (nz + 1) / world
-        # operator_smoother: V(2,2) without a stored direction = (z, r, Dinv -> z') twice and once with z_prev as well
-        per_launch = {"operator_smoother": (32 + 32 + 40) / 3.0 * n_dof_r + 8 * n_cell_r, "operator_residual": 24 * n_dof_r + 8 * n_cell_r,
+        # operator_smoother: V(2,2) without a stored direction = (z, r -> z') twice and once with z_prev as well: 24 / 24 / 32 B/dof,
+        # plus D^-1 as one double per NODE (8/3 B/dof, sweep_kernel.cuh sw_dinv) and the modulus
+        per_launch = {"operator_smoother": ((24 + 24 + 32) / 3.0 + 8.0 / 3.0) * n_dof_r + 8 * n_cell_r, "operator_residual": 24 * n_dof_r + 8 * n_cell_r,
                       "filter_stencil": 24 * n_cell_r, "sens_energy": 8 * n_dof_r + 16 * n_cell_r, "oc_volumes": 16 * n_cell_r,
                       "prolong_fine": (16 + 1 + 1 / 3) * n_dof_r, "restrict_fine": (8 + 1) * n_dof_r, "mg_update_first": 40 * n_dof_r,
                       "mg_direction": 40 * n_dof_r}

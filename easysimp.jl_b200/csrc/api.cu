@@ -899,13 +899,33 @@ int esimp_bench_operator_mode(esimp_ctx* ctx, int mode, int reps, double* ms_avg
     ESIMP_CUDA(cudaMemcpyAsync(ctx->d_r, ctx->d_p, sizeof(double) * ctx->ndof_loc, cudaMemcpyDeviceToDevice, ctx->stream));
     ESIMP_CUDA(cudaMemsetAsync(ctx->d_u, 0, sizeof(double) * ctx->ndof_loc, ctx->stream));
     const OpView vw = fine_view(ctx);
+    double* d_sinv = nullptr;  // the smoother modes of the sweep kernel read D^-1 as one double per node
+    if ((mode == 2 || mode == 4) && hex8_sweep_eligible(ctx, vw)) {
+        ESIMP_CUDA(cudaMalloc(&d_sinv, sizeof(double) * ctx->g.NPX * ctx->g.plane));
+        ESIMP_CUDA(cudaMemsetAsync(d_sinv, 0, sizeof(double) * ctx->g.NPX * ctx->g.plane, ctx->stream));
+        int s = hex8_node_scalar_dinv(ctx, vw, ctx->d_dinv, d_sinv);
+        if (s < 0) {
+            cudaFree(d_sinv);
+            return s;
+        }
+    }
+    struct FreeOnExit {
+        double* p;
+        cudaStream_t st;
+        ~FreeOnExit() {
+            if (p) {
+                cudaStreamSynchronize(st);
+                cudaFree(p);
+            }
+        }
+    } free_sinv{d_sinv, ctx->stream};
     auto run = [&]() -> int {
         switch (mode) {
             case 0: return hex8_matvec_view(ctx, vw, ctx->d_p, ctx->d_q, ctx->prm.matvec_variant, -1);
             case 1: return hex8_matvec_view(ctx, vw, ctx->d_p, ctx->d_q, ctx->prm.matvec_variant, SC_PQ);
-            case 2: return hex8_smooth_view(ctx, vw, ctx->d_p, ctx->d_q, ctx->d_r, ctx->d_dinv, ctx->d_u, 0.3, 0.7, -1);
+            case 2: return hex8_smooth_view(ctx, vw, ctx->d_p, ctx->d_q, ctx->d_r, ctx->d_dinv, ctx->d_u, 0.3, 0.7, -1, 1, 1, nullptr, d_sinv);
             case 3: return hex8_resid_view(ctx, vw, ctx->d_p, ctx->d_q, ctx->d_r);
-            default: return hex8_smooth_view(ctx, vw, ctx->d_p, ctx->d_q, ctx->d_r, ctx->d_dinv, ctx->d_u, 0.3, 0.7, SC_PQ);
+            default: return hex8_smooth_view(ctx, vw, ctx->d_p, ctx->d_q, ctx->d_r, ctx->d_dinv, ctx->d_u, 0.3, 0.7, SC_PQ, 1, 1, nullptr, d_sinv);
         }
     };
     ESIMP_TRY(run());  // warm-up
@@ -918,7 +938,8 @@ int esimp_bench_operator_mode(esimp_ctx* ctx, int mode, int reps, double* ms_avg
     if (ms_avg) *ms_avg = ms / reps;
     if (bytes_per_apply) {
         const double dofs = 3.0 * (ctx->own_p1 - ctx->own_p0) * (double)(ctx->g.ny + 1) * (double)(ctx->g.nz + 1);
-        const double per_dof = mode <= 1 ? 16.0 : (mode == 3 ? 24.0 : 48.0);
+        // smoother modes: z, r, d read, z', d written (40 B/dof) + D^-1 (8 B per node = 2.67 B/dof on the sweep kernel, 8 B/dof on the round-1 kernel)
+        const double per_dof = mode <= 1 ? 16.0 : (mode == 3 ? 24.0 : (d_sinv ? 40.0 + 8.0 / 3.0 : 48.0));
         *bytes_per_apply = per_dof * dofs + 8.0 * (double)(ctx->own_cell1 - ctx->own_cell0);
     }
     ESIMP_CUDA(cudaMemsetAsync(ctx->d_u, 0, sizeof(double) * ctx->ndof_loc, ctx->stream));

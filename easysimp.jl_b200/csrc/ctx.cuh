@@ -50,6 +50,7 @@ struct MGLevel {
     long long* d_fixed = nullptr;
     long long n_fixed = 0;
     double* d_dinv = nullptr;
+    double* d_sinv = nullptr;  // node scalar form of d_dinv for the sweep kernel's smoother modes (hex8_node_scalar_dinv)
     double diag_value = 1.0, lmax = 4.0;
     double *d_r = nullptr, *d_z = nullptr, *d_d = nullptr, *d_q = nullptr;  // rhs, correction, Chebyshev direction, A z
     double* d_z2 = nullptr;  // second buffer of the correction: the fused smoother writes z' while neighbours still read z
@@ -249,7 +250,11 @@ int hex8_diagonal_view(esimp_ctx* ctx, const OpView& vw, double* dinv, long long
 // dmode (FUSE_D_* of fused_kernel.cuh): 1 = the previous direction is read from d, 2 = it is z_in itself (first step after a zero guess),
 // 3 = it is z_in - zprev (zprev may alias z_out); write_d = 0 drops the store of the new direction
 int hex8_smooth_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double* z_out, const double* r, const double* dinv,
-                     double* d, double c1, double c2, int dot_slot = -1, int dmode = 1, int write_d = 1, const double* zprev = nullptr);
+                     double* d, double c1, double c2, int dot_slot = -1, int dmode = 1, int write_d = 1, const double* zprev = nullptr,
+                     const double* sinv = nullptr);
+// D^-1 of a view as ONE double per node ([NPX][ny+1][nzp]): 1 / (sum of E around the node) with the prescribed-component mask in the
+// three lowest mantissa bits -- what the sweep kernel's smoother modes read instead of the three-component dinv (8 instead of 24 B/node)
+int hex8_node_scalar_dinv(esimp_ctx* ctx, const OpView& vw, const double* dinv, double* sinv);
 int hex8_resid_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double* res_out, const double* r);
 bool hex8_sweep_eligible(const esimp_ctx* ctx, const OpView& vw);
 int hex8_smooth_view_f32(esimp_ctx* ctx, const OpView& vw, const float* E, const float* z_in, float* z_out, const float* r,

@@ -155,6 +155,7 @@ struct FuseArgsT {
     int dmode = FUSE_D_BUFFER;   // where the previous Chebyshev direction comes from (ignored when c1 == 0)
     int write_d = 1;             // store the new direction into d
     const T* zprev = nullptr;    // FUSE_D_FROM_ZPREV: the iterate before z (may alias the output vector)
+    const T* sinv = nullptr;     // sweep kernel only: D^-1 as one double per node (sweep_kernel.cuh, sw_dinv); this kernel reads dinv
 };
 using FuseArgs = FuseArgsT<double>;
 // T = double: the operator of the FP64 solve.  T = float: the same kernel for the single-precision multigrid cycle

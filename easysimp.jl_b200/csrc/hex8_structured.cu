@@ -380,11 +380,13 @@ static int launch_sweep_r(esimp_ctx* ctx, const OpView& vw, bool fine, const dou
     ESIMP_TRY(make_map3(ctx, &tmU, d_in, nz1, ny1, n3, g.nzp, g.plane, SW_BOXZ, SW_ROWS, 3));
     ESIMP_TRY(make_map3(ctx, &tmE, vw.E, g.nz, g.ny, g.NEX, g.nz, g.eplane, 32, SW_CROWS, 1));
     for (int b = 0; b < 3; ++b) tmOp[b] = tmOpx[b] = tmU;
-    const double* ops[3] = {fa.r, fa.dinv, fa.dmode == FUSE_D_FROM_ZPREV ? fa.zprev : fa.d};
+    const double* ops[3] = {fa.r, fa.sinv, fa.dmode == FUSE_D_FROM_ZPREV ? fa.zprev : fa.d};
     for (int b = 0; b < TR::NF; ++b) {  // r | r, Dinv, d: exactly the owned nodes of a segment, and the extra column nz
-        ESIMP_TRY(make_map3(ctx, &tmOp[b], ops[b], nz1, ny1, n3, g.nzp, g.plane, 32, SW_OROWS, 3));
-        ESIMP_TRY(make_map3(ctx, &tmOpx[b], ops[b], nz1, ny1, n3, g.nzp, g.plane, 2, SW_OROWS, 3));
+        const bool scalar = TR::NF > 1 && b == 1;  // D^-1 travels as one double per node (sw_dinv): planes of [ny+1][nzp], one per x plane
+        ESIMP_TRY(make_map3(ctx, &tmOp[b], ops[b], nz1, ny1, scalar ? (cuuint64_t)g.NPX : n3, g.nzp, g.plane, 32, SW_OROWS, scalar ? 1 : 3));
+        ESIMP_TRY(make_map3(ctx, &tmOpx[b], ops[b], nz1, ny1, scalar ? (cuuint64_t)g.NPX : n3, g.nzp, g.plane, 2, SW_OROWS, scalar ? 1 : 3));
     }
+    for (int c = 0; c < 3; ++c) a.ik[c] = 1.0 / ctx->kdiag[c];
     const bool timed = ctx->prof_on >= (MODE <= FUSE_DOT ? 1 : 2) && fine && 2 * ctx->prof_n + 1 < (int)ctx->prof_ev.size();
     if (timed) ctx->prof_tag[ctx->prof_n] = MODE <= FUSE_DOT ? PROF_OP_PLAIN : (MODE == FUSE_RESID ? PROF_OP_RESID : PROF_OP_SMOOTH);
     if (timed) cudaEventRecord(ctx->prof_ev[2 * ctx->prof_n], ctx->stream);
@@ -450,11 +452,12 @@ int hex8_matvec_view(esimp_ctx* ctx, const OpView& vw, const double* d_in, doubl
 }
 // multigrid smoother step / residual fused into the operator's store (16x16 owner tiles: measured faster than 8x16 for these modes)
 int hex8_smooth_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, double* z_out, const double* r, const double* dinv,
-                     double* d, double c1, double c2, int dot_slot, int dmode, int write_d, const double* zprev) {
+                     double* d, double c1, double c2, int dot_slot, int dmode, int write_d, const double* zprev, const double* sinv) {
     ESIMP_TRY(hex8_upload_constants(ctx));
     FuseArgs fa;
     fa.r = r;
     fa.dinv = dinv;
+    fa.sinv = sinv;
     fa.d = d;
     fa.c1 = c1;
     fa.c2 = c2;
@@ -465,7 +468,7 @@ int hex8_smooth_view(esimp_ctx* ctx, const OpView& vw, const double* z_in, doubl
     // round-1 kernel at 512x256x256); with 64-byte granules it is the faster one (inside the SIMP step: 0.90 ms against 1.15 ms per
     // smoother launch, profiles/README.md).  ESIMP_SWEEP_SMOOTH=0 goes back to the round-1 kernel for these modes.
     static const int sweep_smooth = getenv("ESIMP_SWEEP_SMOOTH") ? atoi(getenv("ESIMP_SWEEP_SMOOTH")) : 1;
-    if ((sweep_smooth || ctx->prm.matvec_variant == ESIMP_MATVEC_SWEEP) && hex8_sweep_eligible(ctx, vw)) {
+    if (sinv && (sweep_smooth || ctx->prm.matvec_variant == ESIMP_MATVEC_SWEEP) && hex8_sweep_eligible(ctx, vw)) {
         const bool fine = vw.E == ctx->d_E;
         return dot_slot >= 0 ? launch_sweep<FUSE_SMOOTH_DOT>(ctx, vw, fine, z_in, z_out, dot_slot, fa)
                              : launch_sweep<FUSE_SMOOTH>(ctx, vw, fine, z_in, z_out, -1, fa);
@@ -596,6 +599,31 @@ int hex8_diagonal_view(esimp_ctx* ctx, const OpView& vw, double* dinv, long long
     ESIMP_TRY(fetch_scalars(ctx));
     *diag_value = ctx->h_scal[SC_DIAGSUM] / (double)n_dofs_global;  // mean |diag K| (all entries > 0)
     k_diag_invert<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(vw.g, vw.own_p0, vw.own_p1, vw.mask, *diag_value, dinv);
+    ctx->launches++;
+    ESIMP_CUDA(cudaGetLastError());
+    return ESIMP_OK;
+}
+// sinv[node] = 1 / (sum of E around the node) = dinv[node, c] * K0cc[c] for any component c that is not prescribed, with the node's
+// prescribed-component mask in the three lowest mantissa bits (sweep_kernel.cuh, sw_dinv); pads and fully prescribed nodes: 0 | mask
+__global__ void k_node_sinv(GridDev g, int ps0, int ps1, const uint8_t* __restrict__ mask, const double* __restrict__ dinv,
+                            double* __restrict__ sinv) {
+    const long long n = (long long)(ps1 - ps0) * g.plane;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int lp = ps0 + (int)(i / g.plane);
+        const long long in_plane = i % g.plane;
+        const long long nn = (long long)lp * g.plane + in_plane;
+        const bool pad = (int)(in_plane % g.nzp) > g.nz;
+        const unsigned m = pad ? 7u : (mask[nn] & 7u);
+        double s = 0.0;
+#pragma unroll
+        for (int c = 2; c >= 0; --c)
+            if (!((m >> c) & 1)) s = dinv[((long long)lp * 3 + c) * g.plane + in_plane] * c_kdiag[c];
+        sinv[nn] = __longlong_as_double((__double_as_longlong(s) & ~7ll) | (long long)m);
+    }
+}
+int hex8_node_scalar_dinv(esimp_ctx* ctx, const OpView& vw, const double* dinv, double* sinv) {
+    ESIMP_TRY(hex8_upload_constants(ctx));
+    k_node_sinv<<<RED_BLOCKS, RED_THREADS, 0, ctx->stream>>>(vw.g, vw.own_p0, vw.own_p1, vw.mask, dinv, sinv);
     ctx->launches++;
     ESIMP_CUDA(cudaGetLastError());
     return ESIMP_OK;

@@ -284,6 +284,7 @@ void mg_free(esimp_ctx* ctx) {
     for (size_t l = 0; l < ctx->mg.size(); ++l) {
         MGLevel& L = ctx->mg[l];
         cudaFree(L.d_z);
+        cudaFree(L.d_sinv);
         cudaFree(L.d_z2);
         cudaFree(L.d_d);
         cudaFree(L.d_pi);
@@ -484,6 +485,15 @@ int mg_setup(esimp_ctx* ctx) {
         mg_plan_tail(ctx);
     }
     ctx->mg[0].diag_value = ctx->diag_value;
+    auto node_scalar = [&](MGLevel& L) -> int {  // D^-1 in the form the sweep kernel's smoother modes read (levels it serves only)
+        if (!hex8_sweep_eligible(ctx, L.vw)) return ESIMP_OK;
+        if (!L.d_sinv) {
+            ESIMP_CUDA(cudaMalloc(&L.d_sinv, sizeof(double) * L.vw.g.NPX * L.vw.g.plane));
+            ESIMP_CUDA(cudaMemsetAsync(L.d_sinv, 0, sizeof(double) * L.vw.g.NPX * L.vw.g.plane, ctx->stream));
+        }
+        return hex8_node_scalar_dinv(ctx, L.vw, L.d_dinv, L.d_sinv);
+    };
+    ESIMP_TRY(node_scalar(ctx->mg[0]));
     for (size_t l = 1; l < ctx->mg.size(); ++l) {
         MGLevel &F = ctx->mg[l - 1], &C = ctx->mg[l];
         if (C.replicated && !F.replicated) {
@@ -503,6 +513,7 @@ int mg_setup(esimp_ctx* ctx) {
         }
         LocalScope ls(ctx, C.replicated);
         ESIMP_TRY(hex8_diagonal_view(ctx, C.vw, C.d_dinv, C.n_dofs_global, &C.diag_value));
+        ESIMP_TRY(node_scalar(C));
     }
     for (auto& L : ctx->mg) {
         LocalScope ls(ctx, L.replicated);
@@ -556,7 +567,7 @@ static int mg_smooth(esimp_ctx* ctx, MGLevel& L, int k, bool zero_guess, bool fi
             // the previous direction is never a stored vector: z itself right after the zero-guess first step, z - z_prev later
             // (z_prev = the input of the previous step = d_z2, which this step overwrites in place)
             const int dmode = i == 0 ? FUSE_D_NONE : (i == 1 && zero_guess ? FUSE_D_IS_Z : FUSE_D_FROM_ZPREV);
-            ESIMP_TRY(hex8_smooth_view(ctx, L.vw, L.d_z, L.d_z2, L.d_r, L.d_dinv, L.d_d, c1, c2, with_dot ? dot_slot : -1, dmode, 0, L.d_z2));
+            ESIMP_TRY(hex8_smooth_view(ctx, L.vw, L.d_z, L.d_z2, L.d_r, L.d_dinv, L.d_d, c1, c2, with_dot ? dot_slot : -1, dmode, 0, L.d_z2, L.d_sinv));
             if (with_dot && dot_done) *dot_done = true;
             std::swap(L.d_z, L.d_z2);
         } else {

@@ -202,6 +202,16 @@ inline double sw_shfl_up1(double v) {
     g_warp_barrier[wp]->arrive_and_wait();
     return r;
 }
+inline long long sw_double_as_ll(double v) {
+    long long b;
+    memcpy(&b, &v, 8);
+    return b;
+}
+inline double sw_ll_as_double(long long b) {
+    double v;
+    memcpy(&v, &b, 8);
+    return v;
+}
 inline void sw_regs_producer() {}
 inline void sw_regs_consumer() {}
 inline void sw_consumer_barrier() { g_consumer_barrier->arrive_and_wait(); }
@@ -480,6 +490,15 @@ void emu_set_smoother_direction(int dmode, int write_d, const double* zprev) {
     g_zprev = zprev;
 }
 
+static double g_ik[3] = {1.0, 1.0, 1.0};
+// 1 / K0[3a+c, 3a+c] for the sweep kernel's smoother modes: their `dinv` argument is the NODE scalar array [npx][ny+1][nzp]
+// (s = 1 / sum E with the prescribed-component mask in the three lowest mantissa bits), Dinv[node, c] = ik[c] * s
+void emu_sweep_set_ik(double k0, double k1, double k2) {
+    g_ik[0] = k0;
+    g_ik[1] = k1;
+    g_ik[2] = k2;
+}
+
 // One launch of the sweep kernel (sweep_kernel.cuh) on ONE x-slab (or the whole grid: gp0 = ge0 = 0, npx = nx + 1, nex = nx,
 // [ps0, ps1) = [0, nx + 1), [le0, le1) = [0, nx)).  Vectors in the library's device layout with node-row pitch nzp.
 int emu_sweep(int mode, int nx, int ny, int nz, int nzp, int gp0, int npx, int ge0, int nex, int ps0, int ps1, int le0, int le1, int chunk,
@@ -510,6 +529,7 @@ int emu_sweep(int mode, int nx, int ny, int nz, int nzp, int gp0, int npx, int g
     a.c2 = c2;
     a.dmode = c1 != 0.0 ? g_dmode : FUSE_D_NONE;
     a.write_d = g_write_d;
+    for (int c = 0; c < 3; ++c) a.ik[c] = g_ik[c];
     double dummy = 0.0;
     if (dot) *dot = 0.0;
     a.dot_out = RedOut<1>{{dot ? dot : &dummy}};
@@ -530,8 +550,14 @@ int emu_sweep(int mode, int nx, int ny, int nz, int nzp, int gp0, int npx, int g
         t.box[2] = 3;
         return t;
     };
-    SwTensorMap tmU = node_map(u, SW_BOXZ, SW_ROWS), tmR = node_map(r, 32, SW_OROWS), tmDinv = node_map(dinv, 32, SW_OROWS),
-                tmD = node_map(g_dmode == FUSE_D_FROM_ZPREV ? g_zprev : d, 32, SW_OROWS), tmRx = node_map(r, 2, SW_OROWS), tmDinvx = node_map(dinv, 2, SW_OROWS),
+    auto scalar_map = [&](const double* base, int bz_, int by_) {  // one double per node: [npx][ny+1][nzp]
+        SwTensorMap t = node_map(base, bz_, by_);
+        t.dim[2] = npx;
+        t.box[2] = 1;
+        return t;
+    };
+    SwTensorMap tmU = node_map(u, SW_BOXZ, SW_ROWS), tmR = node_map(r, 32, SW_OROWS), tmDinv = scalar_map(dinv, 32, SW_OROWS),
+                tmD = node_map(g_dmode == FUSE_D_FROM_ZPREV ? g_zprev : d, 32, SW_OROWS), tmRx = node_map(r, 2, SW_OROWS), tmDinvx = scalar_map(dinv, 2, SW_OROWS),
                 tmDx = node_map(g_dmode == FUSE_D_FROM_ZPREV ? g_zprev : d, 2, SW_OROWS), tmE;
     tmE.base = E;
     tmE.dim[0] = nz;

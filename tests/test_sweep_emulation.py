@@ -24,8 +24,30 @@ def emu(request):
     lib = C.CDLL(str(path))
     lib.emu_sweep.argtypes = [C.c_int] * 14 + [D] * 6 + [C.c_double, C.c_double, D, D]
     lib.emu_set_smoother_direction.argtypes = [C.c_int, C.c_int, D]
+    lib.emu_sweep_set_ik.argtypes = [C.c_double] * 3
+    lib.emu_sweep_set_ik(*IK)
     lib.emu_set_deferred_tma(int(request.param == "tma_lands_later"))
     return lib
+
+
+IK = (1.3, 0.7, 2.1)  # stands for 1 / K0[3a+c, 3a+c]
+
+
+def node_dinv(p, seed=11):
+    """D^-1 the way the sweep kernel's smoother modes take it: ONE double per node (s, think 1 / sum of E around the node) with the
+    prescribed-component mask in its three lowest mantissa bits; Dinv[node, c] = 0 if bit c else IK[c] * s.  Returns the dof vector
+    (caller numbering) for the expected values and the node array in the padded device layout for the kernel."""
+    nx, ny, nz = p.nel
+    rng = np.random.default_rng(seed)
+    shape = (nx + 1, ny + 1, nz + 1)
+    sval = 1.0 / (0.5 + rng.random(shape))
+    mask = np.where(rng.random(shape) < 0.15, rng.integers(1, 8, shape), 0).astype(np.int64)
+    bits = (sval.view(np.int64) & ~np.int64(7)) | mask
+    clean = (bits & ~np.int64(7)).view(np.float64)
+    dinv_dev = np.stack([np.where((mask >> c) & 1, 0.0, clean * IK[c]) for c in range(3)], axis=1)  # [plane][c][y][z]
+    sinv = np.zeros((nx + 1, ny + 1, pitch(nz)))
+    sinv[..., :nz + 1] = bits.view(np.float64)
+    return p.from_dev(np.ascontiguousarray(dinv_dev).ravel()), sinv.ravel()
 
 
 def pitch(nz):
@@ -49,11 +71,12 @@ def unpad_rows(v_pad, nel, npx=None):
     return np.ascontiguousarray(a[..., :nz + 1]).ravel(), a[..., nz + 1:]
 
 
-def run(emu, p, mode, u, chunk=0, r=None, dinv=None, d=None, c1=0.0, c2=0.0):
+def run(emu, p, mode, u, chunk=0, r=None, sinv=None, d=None, c1=0.0, c2=0.0):
     nx, ny, nz = p.nel
     y = np.full(3 * (nx + 1) * (ny + 1) * pitch(nz), np.nan)
     dot = np.zeros(1)
-    dv = [None if a is None else pad_rows(p.to_dev(a), p.nel) for a in (r, dinv, d)]
+    dv = [None if a is None else pad_rows(p.to_dev(a), p.nel) for a in (r, None, d)]
+    dv[1] = sinv  # node scalar array, already in the device layout (node_dinv)
     st = emu.emu_sweep(mode, nx, ny, nz, pitch(nz), 0, nx + 1, 0, nx, 0, nx + 1, 0, nx, chunk, ptr(p.B.ravel()), ptr(p.cells_dev(p.E)),
                        ptr(pad_rows(p.to_dev(u), p.nel)), ptr(dv[0]), ptr(dv[1]), ptr(dv[2]), c1, c2, ptr(y), ptr(dot))
     assert st == 0
@@ -84,16 +107,16 @@ def test_plain_and_dot_modes_match_the_assembled_operator(emu, nel, right, chunk
 def test_smoother_and_residual_modes(emu, nel, right, chunk):
     p = Problem(nel, right, seed=1)
     z, r, d = (p.rng.standard_normal(p.nd) for _ in range(3))
-    dinv = 1.0 / (0.5 + p.rng.random(p.nd))
+    dinv, sinv = node_dinv(p)
     Az = p.A(z)
     c1, c2 = 0.37, 0.81
     v = c1 * d + c2 * dinv * (r - Az)
-    y, dnew, _ = run(emu, p, SMOOTH, z, chunk=chunk, r=r, dinv=dinv, d=d, c1=c1, c2=c2)
+    y, dnew, _ = run(emu, p, SMOOTH, z, chunk=chunk, r=r, sinv=sinv, d=d, c1=c1, c2=c2)
     assert relmax(y, z + v) < 1e-12 and relmax(dnew, v) < 1e-12
-    y2, dnew2, dot = run(emu, p, SMOOTH_DOT, z, chunk=chunk, r=r, dinv=dinv, d=d, c1=c1, c2=c2)
+    y2, dnew2, dot = run(emu, p, SMOOTH_DOT, z, chunk=chunk, r=r, sinv=sinv, d=d, c1=c1, c2=c2)
     assert np.array_equal(y2, y) and abs(dot - r @ (z + v)) < 1e-10 * np.abs(r * (z + v)).sum()
     v0 = c2 * dinv * (r - Az)  # c1 = 0 restarts the recurrence: d is not read at all (NaN in, finite out)
-    y, dnew, _ = run(emu, p, SMOOTH, z, chunk=chunk, r=r, dinv=dinv, d=np.full(p.nd, np.nan), c1=0.0, c2=c2)
+    y, dnew, _ = run(emu, p, SMOOTH, z, chunk=chunk, r=r, sinv=sinv, d=np.full(p.nd, np.nan), c1=0.0, c2=c2)
     assert relmax(y, z + v0) < 1e-12 and relmax(dnew, v0) < 1e-12
     y, _, _ = run(emu, p, RESID, z, chunk=chunk, r=r)
     assert relmax(y, r - Az) < 1e-12
@@ -132,20 +155,20 @@ def test_direction_free_smoother_steps(emu, nel, right, chunk):
     (FUSE_D_IS_Z = 2), later it is z - z_prev (FUSE_D_FROM_ZPREV = 3); the d vector is neither read (NaN in) nor written"""
     p = Problem(nel, right, seed=5)
     r = p.rng.standard_normal(p.nd)
-    dinv = 1.0 / (0.5 + p.rng.random(p.nd))
+    dinv, sinv = node_dinv(p)
     c1, c2 = 0.37, 0.81
     z1 = 0.3 * dinv * r                               # first step from a zero guess: d1 = z1
     z2_want = z1 + c1 * z1 + c2 * dinv * (r - p.A(z1))
     emu.emu_set_smoother_direction(2, 0, None)
     try:
-        y, dnew, _ = run(emu, p, SMOOTH, z1, chunk=chunk, r=r, dinv=dinv, d=np.full(p.nd, np.nan), c1=c1, c2=c2)
+        y, dnew, _ = run(emu, p, SMOOTH, z1, chunk=chunk, r=r, sinv=sinv, d=np.full(p.nd, np.nan), c1=c1, c2=c2)
         assert relmax(y, z2_want) < 1e-12 and np.isnan(dnew).all()
         # next step: d2 = z2 - z1, z_prev handed in the device layout of the kernel under test
         z3_want = z2_want + c1 * (z2_want - z1) + c2 * dinv * (r - p.A(z2_want))
         zprev = pad_rows(p.to_dev(z1), p.nel)
         emu.emu_set_smoother_direction(3, 0, ptr(zprev))
         z1, keep = z2_want, zprev  # noqa: F841  (keep the buffer alive during the call)
-        y, dnew, dot = run(emu, p, SMOOTH_DOT, z1, chunk=chunk, r=r, dinv=dinv, d=np.full(p.nd, np.nan), c1=c1, c2=c2)
+        y, dnew, dot = run(emu, p, SMOOTH_DOT, z1, chunk=chunk, r=r, sinv=sinv, d=np.full(p.nd, np.nan), c1=c1, c2=c2)
         assert relmax(y, z3_want) < 1e-12 and np.isnan(dnew).all() and abs(dot - r @ z3_want) < 1e-10 * np.abs(r * z3_want).sum()
     finally:
         emu.emu_set_smoother_direction(1, 1, None)
