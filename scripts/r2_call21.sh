@@ -1,6 +1,9 @@
 #!/bin/bash
 # round 2, GPU call 21: A/B of the FUSE_DOT implementations (variant libraries), sweep smoother vs round-1 smoother inside the step with
 # the 64-byte TMA promotion
+# The variant libraries were built beforehand (not part of `make`): for v in 0 1 2 (a macro of that experiment, removed afterwards: 0 node-by-node dot, 1 mode-space dot, 2 one accumulator per component): nvcc -O3 -std=c++17 -lineinfo -gencode
+# arch=compute_100a,code=sm_100a -Xcompiler -fPIC -DSW_DOT_IMPL=$v -c csrc/hex8_structured.cu -o build/hex8_v$v.o, linked with the other objects
+# of the library into easysimp.jl_b200/variants/*.so and selected with ESIMP_LIB.
 set -u
 mkdir -p gpurun_out
 O=gpurun_out

@@ -1,5 +1,8 @@
 #!/bin/bash
 # round 2, GPU call 23: store-phase operand preloading variants of the sweep kernel (isolated + in step), marching restriction kernel
+# The variant libraries were built beforehand (not part of `make`): for v in 0 1 3 7: nvcc -O3 -std=c++17 -lineinfo -gencode
+# arch=compute_100a,code=sm_100a -Xcompiler -fPIC -DSW_PRELOAD=$v -c csrc/hex8_structured.cu -o build/hex8_v$v.o, linked with the other objects
+# of the library into easysimp.jl_b200/variants/*.so and selected with ESIMP_LIB.
 set -u
 mkdir -p gpurun_out
 O=gpurun_out
