@@ -223,7 +223,9 @@ int esimp_set_grid_structured(esimp_ctx* ctx, int nx, int ny, int nz, double hx,
     ctx->has_left = r > 0;
     ctx->has_right = r < R - 1;
     ctx->halo_e = R > 1 ? std::max(1, (int)floor(ctx->prm.filter_radius / hx + 1e-9)) : 0;
-    if (R > 1 && ex1 - ex0 < ctx->halo_e) return esimp_fail(ctx, ESIMP_ERR_ARG, "slab thinner than the filter halo");
+    // the thinnest slab of the partition (floor(nx / R) layers), not this rank's own: every rank takes the same decision, so a
+    // grid that is too small for the rank count fails on all ranks together instead of leaving the others inside a collective
+    if (R > 1 && nx / R < ctx->halo_e) return esimp_fail(ctx, ESIMP_ERR_ARG, "slab thinner than the filter halo");
     const int left = ctx->has_left ? 1 : 0, right = ctx->has_right ? 1 : 0;
     const int gl = ctx->has_left ? ctx->halo_e : 0, gr = ctx->has_right ? ctx->halo_e : 0;
     GridDev& g = ctx->g;

@@ -686,6 +686,62 @@ def four_legs_problem(nel=(40, 20, 20)):
     return g, dofs, f, prescribed
 
 
+def _nearest_node(grid, target):
+    """The closest-node fallback the example scripts carry (first minimum, 02_sliding_support.jl:74-86)."""
+    return int(np.argmin(np.linalg.norm(grid.coords - np.asarray(target, dtype=np.float64), axis=1)))
+
+
+def sliding_support_problem(nel=(60, 20, 4)):
+    """test/Examples/02_sliding_support.jl:46-118: x = 0 face slides (U1 = 0 only), the nodes
+    select_nodes_by_circle(grid, [Lx, 0, Lz/2], [0,1,0], 0.5) returns carry U2 = 0 only, total force [0,-1,0]
+    on select_nodes_by_circle(grid, [0, Ly, Lz/2], [1,0,0], 1.0).  Partial (per-component) Dirichlet sets."""
+    g = generate_grid_hex(nel, (0.0, 0.0, 0.0), tuple(float(n) for n in nel))
+    dofs = distribute_dofs(g)
+    Lx, Ly, Lz = (float(n) for n in nel)
+    sliding = select_nodes_by_plane(g, [0.0, 0.0, 0.0], [1.0, 0.0, 0.0], 1e-3)
+    support = select_nodes_by_circle(g, [Lx, 0.0, 0.5 * Lz], [0.0, 1.0, 0.0], 0.5) or {_nearest_node(g, [Lx, 0.0, 0.5 * Lz])}
+    force = select_nodes_by_circle(g, [0.0, Ly, 0.5 * Lz], [1.0, 0.0, 0.0], 1.0) or {_nearest_node(g, [0.0, Ly, 0.5 * Lz])}
+    prescribed = np.unique(np.concatenate([dofs[np.array(sorted(sliding)), 0], dofs[np.array(sorted(support)), 1]]))
+    f = apply_point_load(np.zeros(3 * g.n_nodes), dofs, force, [0.0, -1.0, 0.0])
+    return g, dofs, f, prescribed
+
+
+def mbb_problem(nel=(40, 20, 20)):
+    """test/Examples/06_3D_2x1x1_MBB.jl:29,53-113: 2x1x1 box, symmetry face x = 0 (U1 = 0), bottom edge strip
+    y = 0, x >= 1.95 (U2 = 0), the node nearest (0, 1, 0.5) holds U3, total force [0,-1,0] on the half disc
+    r <= 0.1 around (0, 1, 0.5) of the top face."""
+    g = generate_grid_hex(nel, (0.0, 0.0, 0.0), (2.0, 1.0, 1.0))
+    dofs = distribute_dofs(g)
+    x, y, z = g.coords.T
+    eps = np.finfo(np.float64).eps
+    sym = np.nonzero(np.abs(x) < 1e-12)[0]  # select_nodes_by_plane(..., eps()): exact plane on generate_grid coordinates
+    sup = np.nonzero((np.abs(y) < eps) & (x >= 2.0 - 0.05 - eps))[0]
+    zfix = _nearest_node(g, [0.0, 1.0, 0.5])
+    force = np.nonzero((np.abs(y - 1.0) < eps) & (np.sqrt(x ** 2 + (z - 0.5) ** 2) <= 0.1 + eps) & (x >= -eps))[0]
+    prescribed = np.unique(np.concatenate([dofs[sym, 0], dofs[sup, 1], dofs[[zfix], 2]]))
+    f = apply_point_load(np.zeros(3 * g.n_nodes), dofs, force.tolist(), [0.0, -1.0, 0.0])
+    return g, dofs, f, prescribed
+
+
+def michell_half_problem(nel=(40, 20, 20)):
+    """test/Examples/08_3D_2x1x1_Michell-half_tol_study.jl:66,95-164: two clamped 0.2 x 0.2 patches of the bottom
+    face at the corners (0,0,0) and (2,0,0), symmetry plane z = 1 (U3 = 0), total force [0,-1,0] on the disc r <= 0.1
+    around (1, 0, 1) of the bottom face.  Mixes apply_fixed_boundary! and apply_sliding_boundary! handlers."""
+    g = generate_grid_hex(nel, (0.0, 0.0, 0.0), (2.0, 1.0, 1.0))
+    dofs = distribute_dofs(g)
+    x, y, z = g.coords.T
+    eps = np.finfo(np.float64).eps
+    cs = 0.20
+    bottom = np.abs(y) < eps
+    left = np.nonzero(bottom & (x <= cs + eps) & (z <= cs + eps))[0]
+    right = np.nonzero(bottom & (x >= 2.0 - cs - eps) & (z <= cs + eps))[0]
+    symz = np.array(sorted(select_nodes_by_plane(g, [0.0, 0.0, 1.0], [0.0, 0.0, 1.0], 1e-6)))
+    force = np.nonzero(bottom & (np.sqrt((x - 1.0) ** 2 + (z - 1.0) ** 2) <= 0.1 + eps))[0]
+    prescribed = np.unique(np.concatenate([dofs[left].ravel(), dofs[right].ravel(), dofs[symz, 2]]))
+    f = apply_point_load(np.zeros(3 * g.n_nodes), dofs, force.tolist(), [0.0, -1.0, 0.0])
+    return g, dofs, f, prescribed
+
+
 def splitmix64(idx, seed=20261018):
     """Counter-based hash -> U[0,1): bit-identical in C++, CUDA and numpy."""
     with np.errstate(over="ignore"):

@@ -60,6 +60,18 @@ CASES = {
         "c2s_4legs_20x10x10", o.four_legs_problem((20, 10, 10)),
         o.OptimizationParameters(volume_fraction=0.4, max_iterations=25, tolerance=0.0, filter_radius=2.0, filter_type="density"),
         "direct"),
+    # test/Examples/02_sliding_support.jl: per-component constraints (x = 0 face U1 only, one node U2 only), E0 = 200, r 2.0
+    "e02_sliding_support_60x20x4": lambda: run_case(
+        "e02_sliding_support_60x20x4", o.sliding_support_problem((60, 20, 4)),
+        o.OptimizationParameters(E0=200.0, Emin=1e-6, volume_fraction=0.4, max_iterations=30, tolerance=0.0, filter_radius=2.0), "direct"),
+    # test/Examples/06_3D_2x1x1_MBB.jl at half resolution: symmetry face + support strip + one U3 node, half-disc load
+    "e06_mbb_20x10x10": lambda: run_case(
+        "e06_mbb_20x10x10", o.mbb_problem((20, 10, 10)),
+        o.OptimizationParameters(E0=1.0, Emin=1e-6, volume_fraction=0.4, max_iterations=25, tolerance=0.0, filter_radius=2.0), "direct"),
+    # test/Examples/08_3D_2x1x1_Michell-half_tol_study.jl at half resolution: clamped patches + symmetry plane z = 1
+    "e08_michell_half_20x10x10": lambda: run_case(
+        "e08_michell_half_20x10x10", o.michell_half_problem((20, 10, 10)),
+        o.OptimizationParameters(E0=1.0, Emin=1e-9, volume_fraction=0.4, max_iterations=25, tolerance=0.0, filter_radius=2.0), "direct"),
 }
 
 if __name__ == "__main__":

@@ -5,6 +5,8 @@ and -- at BASELINE sizes -- through size-independent properties.
 Tolerances (BASELINE.json north_star): element sensitivities and filters 1e-10 relative;
 per-iteration compliance 1e-6 relative (PCG rtol stated per test); final density L_inf <= 1e-3.
 """
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -184,14 +186,14 @@ def _run_loop(ctx, n_iter):
     return [ctx.iterate() for _ in range(n_iter)]
 
 
-def _golden_case(gpu_ctx_factory, golden_dir, name, problem, pcg_rtol):
+def _golden_case(gpu_ctx_factory, golden_dir, name, problem, pcg_rtol, precond=0, check_max_u=True):
     gz = np.load(golden_dir / f"{name}.npz")
     nel = tuple(int(v) for v in gz["nel"])
     g, dofs, f, pres = problem(nel)
     E0, Emin, nu, p, vf, ratio, move, damp = gz["params"]
     R = ratio * o.estimate_element_size(g)
     ctx = make_ctx(gpu_ctx_factory, g, dofs, pres, E0=E0, Emin=Emin, nu=nu, p=p, volume_fraction=vf, move_limit=move,
-                   damping=damp, filter_radius=R, filter_type=int(gz["filter_type"][0]), pcg_rtol=pcg_rtol, pcg_check_every=10)
+                   damping=damp, filter_radius=R, filter_type=int(gz["filter_type"][0]), pcg_rtol=pcg_rtol, pcg_check_every=10, precond=precond)
     ctx.set_load(f)
     ctx.filter_build_structured()
     n_it = int(gz["max_iterations"][0])
@@ -206,7 +208,8 @@ def _golden_case(gpu_ctx_factory, golden_dir, name, problem, pcg_rtol):
     # compliance, and the Lagrange multiplier the bisection ends on (same midpoints; the |dV| < 1e-6 break may come a step apart)
     n_cells = g.n_cells
     assert np.max(np.abs(np.array([s.grayness for s in stats]) - gz["grayness"])) <= 5.0 / n_cells + 1e-12
-    assert np.max(np.abs(np.array([s.max_u for s in stats]) - gz["max_u"]) / gz["max_u"]) < 1e-6
+    if check_max_u:  # not defined where K(rho) with its constraints is singular (rigid modes left free): any u + null vector solves it
+        assert np.max(np.abs(np.array([s.max_u for s in stats]) - gz["max_u"]) / gz["max_u"]) < 1e-6
     assert np.max(np.abs(np.array([s.lam for s in stats]) - gz["lam"]) / gz["lam"]) < 1e-4
     assert np.max(np.abs(np.array([s.oc_steps for s in stats]) - gz["oc_steps"])) <= 2
     e_fin, v_fin, _ = ctx.final_analysis()
@@ -240,6 +243,21 @@ def test_loop_c2_small_density_filter_golden(gpu_ctx_factory, golden_dir):
 def test_loop_c2_4legs_golden(gpu_ctx_factory, golden_dir):
     """BASELINE config 2: 40x20x20 over 2x1x1, density filter r=2.0."""
     _golden_case(gpu_ctx_factory, golden_dir, "c2_4legs_40x20x20", o.four_legs_problem, 1e-10)
+
+
+@pytest.mark.parametrize("name,problem", [("e02_sliding_support_60x20x4", "sliding_support_problem"), ("e06_mbb_20x10x10", "mbb_problem"),
+                                          ("e08_michell_half_20x10x10", "michell_half_problem")])
+@pytest.mark.parametrize("precond", [0, 1])
+def test_loop_example_scripts_with_sliding_constraints_golden(gpu_ctx_factory, golden_dir, name, problem, precond):
+    """test/Examples/02_sliding_support.jl, 06_3D_2x1x1_MBB.jl, 08_3D_2x1x1_Michell-half_tol_study.jl (the latter two at half
+    resolution): apply_sliding_boundary! handlers, i.e. nodes with one prescribed component, alone and mixed with clamped
+    patches -- the Dirichlet masks of the operator, the diagonal, the multigrid levels and the fix-up see per-component sets.
+    Jacobi and multigrid preconditioner."""
+    # example 02 constrains U1 on the face x = 0 and U2 at ONE node: the z translation and a rotation about the x axis stay free, K is
+    # singular and the load is consistent with it (no resultant along z, no moment about x).  Compliance, sensitivities and densities
+    # do not see the rigid part of u; max|u| does (tests/test_oracle.py::test_sliding_support_example_is_singular_but_consistent)
+    stats, _ = _golden_case(gpu_ctx_factory, golden_dir, name, getattr(o, problem), 1e-10, precond=precond, check_max_u=not name.startswith("e02"))
+    assert max(s.pcg_iters for s in stats) < (400 if precond else 20000)
 
 
 def test_host_api_simp_optimize_matches_oracle():
@@ -505,6 +523,30 @@ def test_operator_properties_c5_full_size(gpu_ctx_factory):
     y[2::3] = 1.0  # rigid z translation
     assert np.abs(ctx.matvec(y)).max() < 1e-10
     ctx.close()
+
+
+def test_host_api_readme_script_c5_full_size():
+    """the reference's README script (README.md:110-153) through the reference-shaped host calls at BASELINE
+    config 5 -- generate_grid(512, 256, 256), setup_problem (Ferrite's first-encounter dof numbering in closed form, operator
+    handle instead of a sparse K), node pickers, assemble / apply_fixed_boundary! on the handle, simp_optimize, create_results_data.
+    The compliance of the first iterations must equal what the same problem gives when it is driven straight through the C ABI in
+    the library's native numbering (bench.py's history, profiles/r2_end_bench_c5_n1.json: PCG rtol 1e-8 on both sides), the
+    volume constraint must hold and the caller-side setup must stay a matter of seconds (scripts/host_mirror_c5.py prints it)."""
+    import sys
+
+    sys.path.insert(0, str(Path(__file__).resolve().parents[1] / "scripts"))
+    import host_mirror_c5
+
+    res = host_mirror_c5.run((512, 256, 256), 2)
+    print(res)
+    assert res["n_dofs"] == 101649411 and res["n_fixed_nodes"] == 257 * 257 and res["n_force_nodes"] == 4
+    native = [6.411570549436242, 2.4987159902172644]
+    for it, e_ref in zip(res["iterations"], native):
+        assert abs(it["energy"] - e_ref) / e_ref < 1e-6
+        assert abs(it["volume"] / (512.0 * 256.0 * 256.0) - 0.5) < 1e-6
+    assert abs(res["final_volume_fraction"] - 0.5) < 1e-6 and res["max_von_mises"] > 0.0 and res["max_displacement"] > 0.0
+    setup = sum(v for k, v in res["host_seconds"].items() if k not in ("simp_optimize", "create_results_data"))
+    assert setup < 120.0
 
 
 def test_error_paths_and_edge_cases(gpu_ctx_factory):

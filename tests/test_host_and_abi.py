@@ -189,6 +189,9 @@ def test_slab_partition_covers_grid():
             assert s.ge0 + s.mv_e0 == s.gp0 and s.ge0 + s.mv_e1 == s.gp0 + s.npx - 1
             assert s.nex == (s.ex1 - s.ex0) + s.halo_e * ((s.rank > 0) + (s.rank < R - 1))
         assert owned_planes == list(range(nx + 1))
+        # the slab-thickness validation of esimp_set_grid_structured uses floor(nx / R), the thinnest slab of the partition, so that
+        # every rank takes the same accept / reject decision (no rank is left waiting inside a collective)
+        assert min(s.ex1 - s.ex0 for s in slabs) == nx // R
 
 
 def test_multigrid_slab_hierarchy_invariants():

@@ -177,9 +177,20 @@ def test_problem_recipes_match_survey():
     assert pres.size == 3 * 21 * 5 and abs(f.sum() + 1.0) < 1e-15 and np.count_nonzero(f) == 4
     g, dofs, f, pres = o.four_legs_problem((40, 20, 20))
     assert g.n_nodes == 18081 and pres.size == 3 * 196 and np.count_nonzero(f) == 13
+    # the example scripts with per-component constraints (02: sliding face + one U2 node; 06: symmetry face, support
+    # strip, one U3 node; 08: two clamped patches + symmetry plane)
+    g, dofs, f, pres = o.sliding_support_problem((60, 20, 4))
+    assert pres.size == 21 * 5 + 1 and np.count_nonzero(f) == 4 and abs(f.sum() + 1.0) < 1e-15
+    x0 = np.nonzero(np.abs(g.coords[:, 0]) < 1e-9)[0]
+    assert np.isin(dofs[x0, 0], pres).all() and not np.isin(dofs[x0, 2], pres).any()
+    g, dofs, f, pres = o.mbb_problem((40, 20, 20))
+    assert pres.size == 21 * 21 + 2 * 21 + 1 and np.count_nonzero(f) == 9 and abs(f.sum() + 1.0) < 1e-15
+    g, dofs, f, pres = o.michell_half_problem((40, 20, 20))
+    assert pres.size == 2 * 3 * 25 + 41 * 21 and np.count_nonzero(f) == 9
 
 
-@pytest.mark.parametrize("name", ["c1_cantilever_60x20x4", "c1b_runtests_60x20x4", "c2s_4legs_20x10x10", "c2_4legs_40x20x20"])
+@pytest.mark.parametrize("name", ["c1_cantilever_60x20x4", "c1b_runtests_60x20x4", "c2s_4legs_20x10x10", "c2_4legs_40x20x20",
+                                  "e02_sliding_support_60x20x4", "e06_mbb_20x10x10", "e08_michell_half_20x10x10"])
 def test_golden_fixture_sanity(golden_dir, name):
     """The committed fixtures are self-consistent oracle outputs: volume constraint met, compliance
     decreasing overall, densities within bounds."""
@@ -192,6 +203,38 @@ def test_golden_fixture_sanity(golden_dir, name):
     assert gz["energy"][-1] < gz["energy"][0]
     fd = gz["final_density"]
     assert fd.size == int(np.prod(nel)) and fd.min() >= 1e-3 - 1e-12 and fd.max() <= 1 + 1e-12
+
+
+def test_sliding_support_example_is_singular_but_consistent(golden_dir):
+    """test/Examples/02_sliding_support.jl leaves two rigid modes free (U1 = 0 on the face x = 0 allows the y / z translations and the
+    rotation about x; one node with U2 = 0 removes one combination): the BC-modified K is singular, the load is orthogonal to its null
+    space.  A direct factorisation and CG then return different members of the solution set -- same compliance, same sensitivities,
+    hence the same designs; max|u| differs.  This is why the GPU golden test of this example does not compare max|u|."""
+    g, dofs, f, pres = o.sliding_support_problem((30, 10, 2))
+    c = g.coords
+    keep = np.ones(3 * g.n_nodes)
+    keep[pres] = 0.0
+    tz = np.zeros(3 * g.n_nodes)
+    tz[dofs[:, 2]] = 1.0
+    rot = np.zeros(3 * g.n_nodes)  # rotation about the x axis through the support node (x = Lx, y = 0, z = Lz / 2): its U2 vanishes there
+    rot[dofs[:, 1]] = -(c[:, 2] - 1.0)
+    rot[dofs[:, 2]] = c[:, 1]
+    k0 = o.unit_element_matrices(g, 0.3, 1.0)
+    E = o.simp_modulus(np.full(g.n_cells, 0.4), 200.0, 1e-6, 3.0)
+    Kbc, fbc, _ = o.apply_dirichlet(o.assemble_stiffness(g, dofs, E, k0), f.copy(), pres)
+    for v in (tz, rot):
+        assert np.all(v[pres] == 0.0)  # compatible with every constraint ...
+        assert np.abs(Kbc @ v).max() < 1e-9 * np.abs(Kbc.diagonal()).max() * np.abs(v).max()  # ... and strain free
+        assert abs(fbc @ v) < 1e-12  # the load does no work on it
+    prm = o.OptimizationParameters(E0=200.0, Emin=1e-6, volume_fraction=0.4, max_iterations=3, tolerance=0.0, filter_radius=2.0)
+    a = o.simp_optimize(g, dofs, f, pres, prm, solver="direct")
+    b = o.simp_optimize(g, dofs, f, pres, prm, solver="pcg", pcg_rtol=1e-11)
+    ea, eb = (np.array([h.energy for h in r["history"]]) for r in (a, b))
+    assert np.max(np.abs(ea - eb) / ea) < 1e-8
+    assert np.abs(a["densities"] - b["densities"]).max() < 1e-6
+    # and the committed fixture of the full-size example was produced by the direct path: PCG reproduces its compliance
+    gz = np.load(golden_dir / "e02_sliding_support_60x20x4.npz")
+    assert gz["energy"].size == 30 and gz["energy"][-1] < 0.2 * gz["energy"][0]
 
 
 def test_golden_fixture_reproduces_first_iterations(golden_dir):
