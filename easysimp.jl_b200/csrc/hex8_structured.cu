@@ -37,6 +37,7 @@ static const esimp_ctx* g_const_owner_f32[64] = {};  // per device  // owner of 
 
 #include "fused_kernel.cuh"
 #include "sweep_kernel.cuh"
+#include "sweep1_kernel.cuh"
 
 
 static const double HEXREF[8][3] = {{-1, -1, -1}, {1, -1, -1}, {1, 1, -1}, {-1, 1, -1},
@@ -314,10 +315,20 @@ bool hex8_sweep_eligible(const esimp_ctx* ctx, const OpView& vw) {
     if (v == ESIMP_MATVEC_SWEEP) return true;                // asked for by name: any size (tests)
     return g.nz >= 64 && g.ny >= 30 && vw.own_p1 - vw.own_p0 >= 8;
 }
-template <int MODE, int RING>
+template <int MODE, int RING, int NW1>
+static auto sweep_kernel_ptr() {
+    if constexpr (NW1 == 0)
+        return k_matvec_sweep<MODE, RING>;
+    else
+        return k_matvec_sweep1<MODE, RING, NW1>;
+}
+// NW1 = 0: k_matvec_sweep (two cells per thread, 8 consumer warps); NW1 = 16 | 12: k_matvec_sweep1 (one cell per thread, NW1 consumer warps)
+template <int MODE, int RING, int NW1 = 0>
 static int launch_sweep_r(esimp_ctx* ctx, const OpView& vw, bool fine, const double* d_in, double* d_out, int dot_slot, const FuseArgs& fa) {
     using TR = SweepTraits<MODE>;
-    using Smem = SweepSmem<TR::NF, RING>;
+    using Smem = std::conditional_t<NW1 == 0, SweepSmem<TR::NF, RING>, Sweep1Smem<TR::NF, RING, NW1 == 0 ? 16 : NW1>>;
+    constexpr int SW_CROWS = NW1 == 0 ? ::SW_CROWS : NW1, SW_ROWS = SW_CROWS + 1, SW_OROWS = SW_CROWS - 1, SW_CARRY_ROW = SW_CROWS * 3;
+    constexpr int SW_THREADS = NW1 == 0 ? ::SW_THREADS : 32 * (NW1 + S1_PW);
     const GridDev& g = vw.g;
     const int nplanes = vw.own_p1 - vw.own_p0;
     const int nty = (g.ny + 1 + SW_CROWS - 2) / (SW_CROWS - 1);
@@ -344,7 +355,7 @@ static int launch_sweep_r(esimp_ctx* ctx, const OpView& vw, bool fine, const dou
     const int nchunk = (nplanes + chunk - 1) / chunk;
     const size_t smem = sizeof(Smem) + (size_t)(chunk + 3) * SW_CARRY_ROW * 8;
     static std::atomic<unsigned long long> attr_devices{0};
-    auto kern = k_matvec_sweep<MODE, RING>;
+    auto kern = sweep_kernel_ptr<MODE, RING, NW1>();
     const unsigned long long dev_bit = 1ull << (ctx->device & 63);
     if (!(attr_devices.load() & dev_bit)) {
         ESIMP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_limit));
@@ -400,6 +411,14 @@ static int launch_sweep_r(esimp_ctx* ctx, const OpView& vw, bool fine, const dou
 template <int MODE>
 static int launch_sweep(esimp_ctx* ctx, const OpView& vw, bool fine, const double* d_in, double* d_out, int dot_slot, const FuseArgs& fa) {
     static const int ring = getenv("ESIMP_SWEEP_RING") ? atoi(getenv("ESIMP_SWEEP_RING")) : 0;  // tuning: depth of the input ring
+    // ESIMP_SWEEP_CPT1=12: one cell per thread with 12 consumer warps (sweep1_kernel.cuh) instead of two cells per thread with 8.  An
+    // experiment that LOST on the B200 (profiles/r2_one_cell_per_thread_sweep_isolated.log, 512x256x256, ms per launch, plain / +dot /
+    // smoother / residual / smoother+dot): 0.66 / 0.68 / 1.18 / 0.76 / 1.25 against 0.56 / 0.63 / 0.96 / 0.67 / 1.02 for the default kernel;
+    // with 16 consumer warps (112 registers, spills) 0.74 / 1.07 / 2.04 / 1.12 / 2.29.  Parity is green (same log set); it stays as an
+    // opt-in so that the measurement can be repeated.  ESIMP_SWEEP_CPT1_MODES: bit mask of the store modes that take it (default all)
+    static const int cpt1 = getenv("ESIMP_SWEEP_CPT1") ? atoi(getenv("ESIMP_SWEEP_CPT1")) : 0;
+    static const int cpt1_modes = getenv("ESIMP_SWEEP_CPT1_MODES") ? atoi(getenv("ESIMP_SWEEP_CPT1_MODES")) : 31;
+    if (cpt1 == 12 && ((cpt1_modes >> MODE) & 1)) return launch_sweep_r<MODE, SweepTraits<MODE>::RING, 12>(ctx, vw, fine, d_in, d_out, dot_slot, fa);
     if (SweepTraits<MODE>::NF == 0) {
         if (ring == 4) return launch_sweep_r<MODE, 4>(ctx, vw, fine, d_in, d_out, dot_slot, fa);
         if (ring == 6) return launch_sweep_r<MODE, 6>(ctx, vw, fine, d_in, d_out, dot_slot, fa);

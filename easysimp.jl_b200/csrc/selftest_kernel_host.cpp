@@ -221,6 +221,12 @@ inline void sw_consumer_barrier() { g_consumer_barrier->arrive_and_wait(); }
 alignas(128) unsigned char sw_smem_raw[512 * 1024];
 #define SW_SMEM_DECL
 #include "sweep_kernel.cuh"
+template <int NW>
+inline void sw1_consumer_barrier() { g_consumer_barrier->arrive_and_wait(); }
+inline void sw1_regs_producer() {}
+template <int NW>
+inline void sw1_regs_consumer() {}
+#include "sweep1_kernel.cuh"
 
 namespace {
 
@@ -491,6 +497,8 @@ void emu_set_smoother_direction(int dmode, int write_d, const double* zprev) {
 }
 
 static double g_ik[3] = {1.0, 1.0, 1.0};
+static int g_sweep_nw = 0;  // 0: the two-cells-per-thread kernel (sweep_kernel.cuh); 12 / 16: sweep1_kernel.cuh with that many consumer warps
+void emu_sweep_set_variant(int nw) { g_sweep_nw = nw; }
 // 1 / K0[3a+c, 3a+c] for the sweep kernel's smoother modes: their `dinv` argument is the NODE scalar array [npx][ny+1][nzp]
 // (s = 1 / sum E with the prescribed-component mask in the three lowest mantissa bits), Dinv[node, c] = ik[c] * s
 void emu_sweep_set_ik(double k0, double k1, double k2) {
@@ -556,9 +564,12 @@ int emu_sweep(int mode, int nx, int ny, int nz, int nzp, int gp0, int npx, int g
         t.box[2] = 1;
         return t;
     };
-    SwTensorMap tmU = node_map(u, SW_BOXZ, SW_ROWS), tmR = node_map(r, 32, SW_OROWS), tmDinv = scalar_map(dinv, 32, SW_OROWS),
-                tmD = node_map(g_dmode == FUSE_D_FROM_ZPREV ? g_zprev : d, 32, SW_OROWS), tmRx = node_map(r, 2, SW_OROWS), tmDinvx = scalar_map(dinv, 2, SW_OROWS),
-                tmDx = node_map(g_dmode == FUSE_D_FROM_ZPREV ? g_zprev : d, 2, SW_OROWS), tmE;
+    const int nw1 = g_sweep_nw;  // geometry of the kernel that runs
+    const int crows = nw1 ? nw1 : SW_CROWS, rows = crows + 1, orows = crows - 1, nthreads = nw1 ? 32 * (nw1 + 4) : SW_THREADS, ncons = nw1 ? nw1 : SW_NW;
+    if (nw1 != 0 && nw1 != 12 && nw1 != 16) return -1;
+    SwTensorMap tmU = node_map(u, SW_BOXZ, rows), tmR = node_map(r, 32, orows), tmDinv = scalar_map(dinv, 32, orows),
+                tmD = node_map(g_dmode == FUSE_D_FROM_ZPREV ? g_zprev : d, 32, orows), tmRx = node_map(r, 2, orows), tmDinvx = scalar_map(dinv, 2, orows),
+                tmDx = node_map(g_dmode == FUSE_D_FROM_ZPREV ? g_zprev : d, 2, orows), tmE;
     tmE.base = E;
     tmE.dim[0] = nz;
     tmE.dim[1] = ny;
@@ -567,17 +578,17 @@ int emu_sweep(int mode, int nx, int ny, int nz, int nzp, int gp0, int npx, int g
     tmE.stride[1] = nz;
     tmE.stride[2] = g.eplane;
     tmE.box[0] = 32;
-    tmE.box[1] = SW_CROWS;
+    tmE.box[1] = crows;
     tmE.box[2] = 1;
-    const int nty = (ny + 1 + SW_CROWS - 2) / (SW_CROWS - 1), nchunk = (nplanes + a.chunk - 1) / a.chunk;
+    const int nty = (ny + 1 + crows - 2) / (crows - 1), nchunk = (nplanes + a.chunk - 1) / a.chunk;
     gridDim = EmuDim3{(unsigned)nty, (unsigned)nchunk, 1};
-    blockDim = EmuDim3{(unsigned)SW_THREADS, 1, 1};
+    blockDim = EmuDim3{(unsigned)nthreads, 1, 1};
     g_warp_barrier.clear();
-    for (int wi = 0; wi < SW_THREADS / 32; ++wi) g_warp_barrier.emplace_back(new std::barrier<>(32));
+    for (int wi = 0; wi < nthreads / 32; ++wi) g_warp_barrier.emplace_back(new std::barrier<>(32));
     for (int by = 0; by < nchunk; ++by)
         for (int bx = 0; bx < nty; ++bx) {
             blockIdx = EmuDim3{(unsigned)bx, (unsigned)by, 0};
-            std::barrier<> barrier(SW_THREADS), cbarrier(32 * SW_NW);
+            std::barrier<> barrier(nthreads), cbarrier(32 * ncons);
             g_barrier = &barrier;
             g_consumer_barrier = &cbarrier;
             std::atomic<bool> done{false};
@@ -604,10 +615,27 @@ int emu_sweep(int mode, int nx, int ny, int nz, int nzp, int gp0, int npx, int g
                 }
             });
             std::vector<std::thread> threads;
-            threads.reserve(SW_THREADS);
-            for (int t = 0; t < SW_THREADS; ++t)
+            threads.reserve(nthreads);
+            for (int t = 0; t < nthreads; ++t)
                 threads.emplace_back([&, t] {
                     threadIdx = EmuDim3{(unsigned)t, 0, 0};
+#define EMU_SW1(M, N) k_matvec_sweep1<M, SweepTraits<M>::RING, N>(a, tmU, tmE, tmR, tmDinv, tmD, tmRx, tmDinvx, tmDx)
+#define EMU_SW1_MODES(N)                                  \
+    switch (mode) {                                       \
+        case FUSE_PLAIN: EMU_SW1(FUSE_PLAIN, N); break;   \
+        case FUSE_DOT: EMU_SW1(FUSE_DOT, N); break;       \
+        case FUSE_SMOOTH: EMU_SW1(FUSE_SMOOTH, N); break; \
+        case FUSE_RESID: EMU_SW1(FUSE_RESID, N); break;   \
+        case FUSE_SMOOTH_DOT: EMU_SW1(FUSE_SMOOTH_DOT, N); break; \
+    }
+                    if (nw1 == 16) {
+                        EMU_SW1_MODES(16)
+                        return;
+                    }
+                    if (nw1 == 12) {
+                        EMU_SW1_MODES(12)
+                        return;
+                    }
                     switch (mode) {
                         case FUSE_PLAIN: k_matvec_sweep<FUSE_PLAIN, SweepTraits<FUSE_PLAIN>::RING>(a, tmU, tmE, tmR, tmDinv, tmD, tmRx, tmDinvx, tmDx); break;
                         case FUSE_DOT: k_matvec_sweep<FUSE_DOT, SweepTraits<FUSE_DOT>::RING>(a, tmU, tmE, tmR, tmDinv, tmD, tmRx, tmDinvx, tmDx); break;

@@ -17,16 +17,21 @@ ROOT = Path(__file__).resolve().parents[1]
 D = C.POINTER(C.c_double)
 
 
-@pytest.fixture(scope="module", params=["tma_lands_at_issue", "tma_lands_later"])
+# kernel under test: the two-cells-per-thread sweep kernel (8 consumer warps, tiles of 15 owned node rows) and its one-cell-per-thread
+# sibling csrc/sweep1_kernel.cuh with 16 / 12 consumer warps (tiles of 15 / 11 owned node rows)
+@pytest.fixture(scope="module", params=[("tma_lands_at_issue", 0), ("tma_lands_later", 0), ("tma_lands_at_issue", 12), ("tma_lands_later", 16)],
+                ids=lambda p: f"{p[0]}-{'two_cells' if p[1] == 0 else 'one_cell_%d_warps' % p[1]}")
 def emu(request):
     path = ROOT / "easysimp.jl_b200" / "libesimp_kernel_emu.so"
     assert path.exists(), "run __graft_entry__.build() first"
     lib = C.CDLL(str(path))
+    lib.emu_sweep_set_variant.argtypes = [C.c_int]
+    lib.emu_sweep_set_variant(request.param[1])
     lib.emu_sweep.argtypes = [C.c_int] * 14 + [D] * 6 + [C.c_double, C.c_double, D, D]
     lib.emu_set_smoother_direction.argtypes = [C.c_int, C.c_int, D]
     lib.emu_sweep_set_ik.argtypes = [C.c_double] * 3
     lib.emu_sweep_set_ik(*IK)
-    lib.emu_set_deferred_tma(int(request.param == "tma_lands_later"))
+    lib.emu_set_deferred_tma(int(request.param[0] == "tma_lands_later"))
     return lib
 
 
