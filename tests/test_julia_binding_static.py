@@ -185,3 +185,24 @@ def test_binding_defines_the_reference_entry_points():
         assert re.search(pattern, text), pattern
     # 1-based Julia indices are shifted exactly where dofs / cells cross the boundary
     assert re.search(r"prescribed[^\n]*\.- 1", text) and "cell[] + 1" in text
+
+
+def test_julia_source_block_structure_balances():
+    """No Julia parser here; the cheapest structural check that still catches a lost `end` or bracket: with strings, docstrings,
+    comments and index expressions removed, block openers and `end`s pair up, and (), [], {} balance."""
+    t = JULIA.read_text()
+    t = re.sub(r'"""(.*?)"""', '""', t, flags=re.S)
+    t = re.sub(r'"(\\.|[^"\\])*"', '""', t)
+    t = re.sub(r"#[^\n]*", "", t)
+    for a, b in ("()", "[]", "{}"):
+        assert t.count(a) == t.count(b), f"unbalanced {a}{b}"
+    out, depth = [], 0
+    for ch in t:  # `end` inside [...] is an index, comprehension `for`s live there too
+        depth += ch == "["
+        if depth == 0:
+            out.append(ch)
+        depth -= ch == "]"
+    t = "".join(out)
+    openers = re.findall(r"(?<![\w.:])(function|if|for|while|struct|let|do|begin|try|module|quote|macro)(?![\w!])", t)
+    ends = re.findall(r"(?<![\w.:])end(?![\w!])", t)
+    assert len(openers) == len(ends) and len(openers) > 40
