@@ -10,7 +10,7 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 
-enum { OTHER_IMAD = 0, OTHER_LOGIC = 1, OTHER_LDS = 2, OTHER_SHFL = 3 };
+enum { OTHER_IMAD = 0, OTHER_LOGIC = 1, OTHER_LDS = 2, OTHER_SHFL = 3, OTHER_LOP3 = 4, OTHER_MINMAX = 5 };
 
 template <int NF, int NO, int OTHER, bool DO_F, bool DO_O>
 __global__ void k_mix(double* out, int iters, double a, double b, int seed) {
@@ -44,6 +44,8 @@ __global__ void k_mix(double* out, int iters, double a, double b, int seed) {
                         asm volatile("" ::"d"(v));
                     }
                     if (OTHER == OTHER_SHFL) x[i] = __shfl_up_sync(0xffffffffu, x[i], 1);
+                    if (OTHER == OTHER_LOP3) x[i] = x[i] ^ (x[(i + 1) & 7] & x[(i + 3) & 7]);   // one LOP3
+                    if (OTHER == OTHER_MINMAX) x[i] = max(x[i] + 1u, x[(i + 1) & 7]);            // compare / select class
                 }
             }
         }
@@ -51,6 +53,29 @@ __global__ void k_mix(double* out, int iters, double a, double b, int seed) {
     double s = 0;
 #pragma unroll
     for (int i = 0; i < 8; ++i) s += acc[i] + (double)x[i];
+    if (s == 12345.678) out[0] = s;
+}
+
+// the operator kernel takes its 45 mode-space constants from kernel parameters: every use is an LDCU (uniform load from the constant bank)
+// feeding a DFMA with a uniform-register operand.  Same DFMA count with register operands (CONST = false) or parameter operands (true).
+struct ConstBlock {
+    double c[48];
+};
+template <bool CONST>
+__global__ void k_const(double* out, int iters, const __grid_constant__ ConstBlock blk, double a, double b) {
+    double acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = threadIdx.x * 1e-9 + i;
+#pragma unroll 1
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] = CONST ? fma(acc[i], blk.c[(r * 8 + i) % 45], b) : fma(acc[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += acc[i];
     if (s == 12345.678) out[0] = s;
 }
 
@@ -100,6 +125,17 @@ int main() {
             run<8, 8, OTHER_LDS>("LDS.64", sms, 256, d, iters, false);
             run<8, 8, OTHER_SHFL>("SHFL", sms, 256, d, iters, false);
             run<8, 4, OTHER_LOGIC>("IADD3", sms, 256, d, iters, false);
+            run<8, 8, OTHER_LOP3>("LOP3", sms, 256, d, iters, false);
+            run<8, 4, OTHER_LOP3>("LOP3", sms, 256, d, iters, false);
+            run<8, 8, OTHER_MINMAX>("VIADD+VIMNMX", sms, 256, d, iters, false);
+            {
+                ConstBlock blk;
+                for (int i = 0; i < 48; ++i) blk.c[i] = 1.0000001 + 1e-9 * i;
+                const float tr = time_ms([&] { k_const<false><<<sms, 256>>>(d, iters, blk, 1.0000001, 1e-9); });
+                const float tc = time_ms([&] { k_const<true><<<sms, 256>>>(d, iters, blk, 1.0000001, 1e-9); });
+                printf(" \"64 DFMA per trip with register operands / with kernel-parameter operands (LDCU + uniform register), 2 warps per scheduler\": "
+                       "{\"ms_register\": %.3f, \"ms_constant\": %.3f},\n", tr, tc);
+            }
         } else if (threads == 512) {
             run<8, 8, OTHER_IMAD>("IMAD", sms, 512, d, iters, false);
             run<8, 8, OTHER_LOGIC>("IADD3", sms, 512, d, iters, false);
