@@ -10,7 +10,7 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 
-enum { OTHER_IMAD = 0, OTHER_LOGIC = 1, OTHER_LDS = 2, OTHER_SHFL = 3, OTHER_LOP3 = 4, OTHER_MINMAX = 5 };
+enum { OTHER_IMAD = 0, OTHER_LOGIC = 1, OTHER_LDS = 2, OTHER_SHFL = 3, OTHER_LOP3 = 4, OTHER_MINMAX = 5, OTHER_LEA = 6, OTHER_SHF = 7, OTHER_SETP_SEL = 8 };
 
 template <int NF, int NO, int OTHER, bool DO_F, bool DO_O>
 __global__ void k_mix(double* out, int iters, double a, double b, int seed) {
@@ -45,6 +45,9 @@ __global__ void k_mix(double* out, int iters, double a, double b, int seed) {
                     }
                     if (OTHER == OTHER_SHFL) x[i] = __shfl_up_sync(0xffffffffu, x[i], 1);
                     if (OTHER == OTHER_LOP3) x[i] = x[i] ^ (x[(i + 1) & 7] & x[(i + 3) & 7]);   // one LOP3
+                    if (OTHER == OTHER_LEA) x[i] = (x[i] << 3) + x[(i + 1) & 7];                  // LEA
+                    if (OTHER == OTHER_SHF) x[i] = __funnelshift_l(x[i], x[(i + 1) & 7], 5);      // SHF
+                    if (OTHER == OTHER_SETP_SEL) x[i] = ((int)x[i] < it) ? x[(i + 1) & 7] : x[(i + 3) & 7];  // ISETP + SEL
                     if (OTHER == OTHER_MINMAX) x[i] = max(x[i] + 1u, x[(i + 1) & 7]);            // compare / select class
                 }
             }
@@ -128,6 +131,9 @@ int main() {
             run<8, 8, OTHER_LOP3>("LOP3", sms, 256, d, iters, false);
             run<8, 4, OTHER_LOP3>("LOP3", sms, 256, d, iters, false);
             run<8, 8, OTHER_MINMAX>("VIADD+VIMNMX", sms, 256, d, iters, false);
+            run<8, 4, OTHER_LEA>("LEA", sms, 256, d, iters, false);
+            run<8, 4, OTHER_SHF>("SHF", sms, 256, d, iters, false);
+            run<8, 4, OTHER_SETP_SEL>("ISETP+SEL", sms, 256, d, iters, false);
             {
                 ConstBlock blk;
                 for (int i = 0; i < 48; ++i) blk.c[i] = 1.0000001 + 1e-9 * i;
